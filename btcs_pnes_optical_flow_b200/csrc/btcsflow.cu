@@ -1,0 +1,925 @@
+// libbtcsflow.so -- C-ABI host side (plan, scheduling, streaming) over the sm_100a kernels.
+// Interface contract and the reference file:line each entry point replaces: include/btcsflow.h.
+#include "../../include/btcsflow.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "farneback_kernels.cuh"
+#include "farneback_fast.cuh"
+#include "pc1_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local long long g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail((int)e_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                             \
+    do {                                                                                           \
+        ++g_launches;                                                                              \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail((int)e_, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int cv_round(double v) { return (int)std::nearbyint(v); }  // round half to even (cvRound)
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// cv2.resize INTER_LINEAR coefficient tables, float32 weights
+void resize_table(int dst, int src, std::vector<int>& idx, std::vector<float>& wgt) {
+    idx.resize(dst);
+    wgt.resize(dst);
+    if (dst == src) {
+        for (int d = 0; d < dst; ++d) { idx[d] = d; wgt[d] = 0.f; }
+        return;
+    }
+    const double inv = (double)dst / (double)src;
+    const double scale = 1.0 / inv;
+    for (int d = 0; d < dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int i = (int)std::floor(f);
+        f -= (float)i;
+        if (i < 0) { i = 0; f = 0.f; }
+        if (i >= src - 1) { i = src - 1; f = 0.f; }
+        idx[d] = i;
+        wgt[d] = f;
+    }
+}
+
+// cv2.getGaussianKernel (float32 taps)
+std::vector<float> gaussian_kernel(int ksize, double sigma) {
+    std::vector<float> k(ksize);
+    if (sigma <= 0 && ksize == 3) { k = {0.25f, 0.5f, 0.25f}; return k; }
+    if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+    std::vector<double> d(ksize);
+    double s = 0;
+    const double c = (ksize - 1) * 0.5;
+    for (int i = 0; i < ksize; ++i) { const double x = i - c; d[i] = std::exp(-(x * x) / (2 * sigma * sigma)); s += d[i]; }
+    for (int i = 0; i < ksize; ++i) k[i] = (float)(d[i] / s);
+    return k;
+}
+
+bool invert6(double A[6][6], double inv[6][6]) {
+    double a[6][12];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) { a[i][j] = A[i][j]; a[i][6 + j] = (i == j); }
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r) if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+        if (std::fabs(a[piv][c]) < 1e-300) return false;
+        if (piv != c) for (int j = 0; j < 12; ++j) std::swap(a[piv][j], a[c][j]);
+        const double d = 1.0 / a[c][c];
+        for (int j = 0; j < 12; ++j) a[c][j] *= d;
+        for (int r = 0; r < 6; ++r) {
+            if (r == c) continue;
+            const double f = a[r][c];
+            if (f != 0) for (int j = 0; j < 12; ++j) a[r][j] -= f * a[c][j];
+        }
+    }
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) inv[i][j] = a[i][6 + j];
+    return true;
+}
+
+// FarnebackPrepareGaussian
+bool make_poly_coef(int n, double sigma, bf::PolyCoef& pc) {
+    if (sigma < 1.1920928955078125e-07) sigma = n * 0.3;
+    std::vector<float> g(2 * n + 1), xg(2 * n + 1), xxg(2 * n + 1);
+    double s = 0;
+    for (int x = -n; x <= n; ++x) { g[x + n] = (float)std::exp(-x * x / (2 * sigma * sigma)); s += g[x + n]; }
+    s = 1.0 / s;
+    for (int x = -n; x <= n; ++x) {
+        g[x + n] = (float)(g[x + n] * s);
+        xg[x + n] = (float)(x * g[x + n]);
+        xxg[x + n] = (float)(x * x * g[x + n]);
+    }
+    double G[6][6] = {{0}};
+    for (int y = -n; y <= n; ++y)
+        for (int x = -n; x <= n; ++x) {
+            const float gg = g[y + n] * g[x + n];
+            G[0][0] += gg;
+            G[1][1] += gg * x * x;
+            G[3][3] += gg * x * x * x * x;
+            G[5][5] += gg * x * x * y * y;
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    double inv[6][6];
+    if (!invert6(G, inv)) return false;
+    pc.n = n;
+    for (int k = 0; k <= n; ++k) { pc.g[k] = g[n + k]; pc.xg[k] = xg[n + k]; pc.xxg[k] = xxg[n + k]; }
+    pc.ig11 = (float)inv[1][1];
+    pc.ig03 = (float)inv[0][3];
+    pc.ig33 = (float)inv[3][3];
+    pc.ig55 = (float)inv[5][5];
+    return true;
+}
+
+void make_win_coef(int winsize, int flags, bf::WinCoef& wc) {
+    const int m = winsize / 2;
+    wc.m = m;
+    wc.gauss = (flags & BF_OPTFLOW_FARNEBACK_GAUSSIAN) ? 1 : 0;
+    wc.scale = wc.gauss ? 1.f : (float)(1.0 / ((double)winsize * winsize));
+    const double sigma = m * 0.3;
+    std::vector<float> ker(m + 1);
+    ker[0] = 1.f;
+    double s = 1.0;
+    for (int i = 1; i <= m; ++i) {
+        const float t = (float)std::exp(-i * i / (2 * sigma * sigma));
+        ker[i] = t;
+        s += t * 2;
+    }
+    s = 1.0 / s;
+    for (int i = 0; i <= m; ++i) wc.ker[i] = (float)(ker[i] * s);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct ScaleInfo {
+    int k, w, h, ksize, pitch;
+    double scale, sigma;
+    size_t plane;          // h * pitch
+    // device tables
+    int *ix = nullptr, *iy = nullptr;       // image resize: full-res -> this scale
+    float *ax = nullptr, *ay = nullptr;
+    float* kern = nullptr;                    // pyramid Gaussian taps
+    int *fix = nullptr, *fiy = nullptr;     // flow upsample: next-coarser scale -> this scale
+    float *fax = nullptr, *fay = nullptr;
+    float* I = nullptr;                       // [F][h][pitch]
+    float* R = nullptr;                       // [F][5][h][pitch]
+    float2* flow = nullptr;                   // [B][h][pitch]
+};
+
+template <typename T>
+cudaError_t upload(const std::vector<T>& v, T** out) {
+    cudaError_t e = cudaMalloc((void**)out, std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+}  // namespace
+
+struct bf_plan {
+    bf_params prm;
+    int W, H, B, F, max_rois, device;
+    std::vector<ScaleInfo> sc;  // coarse -> fine
+    bf::PolyCoef pc;
+    bf::WinCoef wc;
+    float* tmp = nullptr;       // [F][H][pitch0]
+    float* M[2] = {nullptr, nullptr};
+    float* axes = nullptr;      // [B][4]
+    float* partial = nullptr;   // [B][max_rois][ncta][4]
+    int ncta_max = 0;
+    size_t bytes = 0;
+    // host-staging path
+    uint8_t* stage[2] = {nullptr, nullptr};
+    float* stage_flow = nullptr;
+    double* d_ex = nullptr; double* d_ey = nullptr; int axes_cap = 0;
+    uint8_t* d_masks = nullptr; size_t masks_cap = 0;
+    float* d_out = nullptr; size_t out_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    bool use_fast = true;
+    // dominant-kernel timing (bf_plan_profile)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
+    size_t prof_used = 0;               // events in use
+    long long prof_pairs = 0;
+};
+
+namespace {
+
+template <typename T>
+int plan_alloc(bf_plan* p, T** ptr, size_t count) {
+    CU(cudaMalloc((void**)ptr, std::max<size_t>(count, 1) * sizeof(T)));
+    p->bytes += count * sizeof(T);
+    return 0;
+}
+
+int validate_params(const bf_params* q, int W, int H) {
+    if (!q) return fail(BF_E_INVALID, "params is NULL");
+    if (W <= 0 || H <= 0) return fail(BF_E_INVALID, "bad image size %dx%d", W, H);
+    if (!(q->pyr_scale < 1.0) || !(q->pyr_scale > 0.0))
+        return fail(BF_E_INVALID,
+                    "(-215:Assertion failed) prev0.size() == next0.size() && prev0.channels() == next0.channels() "
+                    "&& prev0.channels() == 1 && pyrScale_ < 1 (pyr_scale=%g)", q->pyr_scale);
+    if (q->levels < 0 || q->iterations < 0) return fail(BF_E_INVALID, "levels/iterations must be >= 0");
+    if (q->winsize < 1) return fail(BF_E_INVALID, "winsize must be >= 1");
+    if (q->poly_n < 1) return fail(BF_E_INVALID, "poly_n must be >= 1");
+    if (q->poly_n > BF_MAX_POLY_N) return fail(BF_E_UNSUPPORTED, "poly_n=%d > %d not supported", q->poly_n, BF_MAX_POLY_N);
+    if (q->winsize / 2 > BF_MAX_WIN_HALF) return fail(BF_E_UNSUPPORTED, "winsize=%d too large (max %d)", q->winsize, 2 * BF_MAX_WIN_HALF + 1);
+    if (q->flags & BF_OPTFLOW_USE_INITIAL_FLOW)
+        return fail(BF_E_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is not supported (the reference path uses flags=0)");
+    if (q->flags & ~(BF_OPTFLOW_FARNEBACK_GAUSSIAN | BF_OPTFLOW_USE_INITIAL_FLOW))
+        return fail(BF_E_INVALID, "unknown flags 0x%x", q->flags);
+    return 0;
+}
+
+// ---- launches -----------------------------------------------------------------------------------------
+
+template <typename T>
+int launch_pyramid(bf_plan* p, const ScaleInfo& s, const T* src, size_t pitch_bytes, size_t frame_bytes, int nf,
+                   float* out, int out_pitch, size_t out_frame_stride, cudaStream_t st) {
+    const int tmp_pitch = s.pitch;
+    const size_t tmp_stride = (size_t)p->H * tmp_pitch;
+    dim3 b(64, 4);
+    dim3 g1(cdiv(s.w, 64), cdiv(p->H, 4), nf);
+    bf::k_pyr_h<T><<<g1, b, 0, st>>>(src, pitch_bytes, frame_bytes, p->W, p->H, s.w, s.ix, s.ax, s.kern, s.ksize,
+                                      p->tmp, tmp_pitch, tmp_stride);
+    LAUNCH_CHECK();
+    dim3 g2(cdiv(s.w, 64), cdiv(s.h, 4), nf);
+    bf::k_pyr_v<<<g2, b, 0, st>>>(p->tmp, tmp_pitch, tmp_stride, p->H, s.w, s.h, s.iy, s.ay, s.kern, s.ksize, out,
+                                  out_pitch, out_frame_stride);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_polyexp(bf_plan* p, const float* I, int pitch, size_t frame_stride, int w, int h, float* R,
+                   size_t plane_stride, size_t slot_stride, int slot0, int nslots, int nf, const bf::PolyCoef& pc,
+                   bool allow_fast, cudaStream_t st) {
+    if (allow_fast && bf::polyexp_fast_supported(pc.n, pitch)) {
+        bf::launch_polyexp_fast(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
+        LAUNCH_CHECK();
+        return 0;
+    }
+    dim3 g(cdiv(w, bf::kPeTW), cdiv(h, bf::kPeTH), nf);
+    bf::k_polyexp_generic<<<g, 256, 0, st>>>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0,
+                                             nslots, pc);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_update(const bf::UpdateArgs& a, int np, cudaStream_t st) {
+    dim3 b(64, 4);
+    dim3 g(cdiv(a.w, 64), cdiv(a.h, 4), np);
+    bf::k_update<<<g, b, 0, st>>>(a);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int blur_solve_ncta(int w, int h, const bf::WinCoef& wc, bool allow_fast, int pitch) {
+    if (allow_fast && bf::blur_solve_fast_supported(wc, pitch)) return bf::blur_solve_fast_ncta(w, h);
+    return cdiv(w, bf::kBsTW) * cdiv(h, bf::kBsTH);
+}
+
+int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast, cudaStream_t st) {
+    if (allow_fast && bf::blur_solve_fast_supported(wc, a.pitch)) {
+        bf::launch_blur_solve_fast(a, wc, np, st);
+        LAUNCH_CHECK();
+        return 0;
+    }
+    dim3 g(cdiv(a.w, bf::kBsTW), cdiv(a.h, bf::kBsTH), np);
+    bf::k_blur_solve_generic<<<g, 256, 0, st>>>(a, wc);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// Pyramid + polynomial expansion of nf frames whose first frame index is tf (ring slot = frame % F).
+template <typename T>
+int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_bytes, int tf, int nf,
+                  cudaStream_t st) {
+    for (auto& s : p->sc) {
+        int rc = launch_pyramid<T>(p, s, frames, pitch_bytes, frame_bytes, nf, s.I, s.pitch, s.plane, st);
+        if (rc) return rc;
+        rc = launch_polyexp(p, s.I, s.pitch, s.plane, s.w, s.h, s.R, s.plane, 5 * s.plane, tf % p->F, p->F, nf,
+                            p->pc, p->use_fast, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+struct RoiCtx {
+    const uint8_t* masks = nullptr;  // [n_roi][H][W]
+    int n_roi = 0;
+    const double* ex = nullptr;      // device [T][2]
+    const double* ey = nullptr;
+    float* out = nullptr;            // device [n_roi][T][3]
+    int T = 0;
+};
+
+// Coarse-to-fine schedule for np pairs whose first frame is t0 (pair q = frames t0+q, t0+q+1).
+// flow_out: dense [np][H][W][2] or NULL.  roi: optional ROI reduction into roi->out rows t0+1+q.
+int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cudaStream_t st) {
+    const int I = p->prm.iterations;
+    const int nsc = (int)p->sc.size();
+    const int slot0 = t0 % p->F;
+    const bool want_roi = roi && roi->n_roi > 0;
+    if (want_roi) {
+        bf::k_axes_to_f32<<<cdiv(np, 64), 64, 0, st>>>(roi->ex, roi->ey, t0 + 1, np, p->axes);
+        LAUNCH_CHECK();
+    }
+    if (I == 0) {
+        // cv2 leaves the (zero-initialised, upsampled) flow untouched: the result is identically zero
+        const ScaleInfo& s = p->sc.back();
+        if (flow_out) CU(cudaMemsetAsync(flow_out, 0, (size_t)np * p->H * p->W * sizeof(float2), st));
+        if (want_roi) {
+            CU(cudaMemsetAsync(s.flow, 0, (size_t)np * s.plane * sizeof(float2), st));
+            bf::BlurSolveArgs a{};
+            a.w = s.w; a.h = s.h; a.pitch = s.pitch;
+            a.flow = s.flow; a.flow_pitch = s.pitch; a.flow_stride = s.plane;
+            a.masks = roi->masks; a.n_roi = roi->n_roi; a.mask_stride = (size_t)p->H * p->W; a.mask_pitch = p->W;
+            a.axes = p->axes; a.partial = p->partial;
+            dim3 g(cdiv(s.w, bf::kBsTW), cdiv(s.h, bf::kBsTH), np);
+            bf::k_roi_from_flow<<<g, 256, 0, st>>>(a);
+            LAUNCH_CHECK();
+            const int ncta = g.x * g.y;
+            bf::k_roi_finalize<<<cdiv(np * roi->n_roi, 64), 64, 0, st>>>(p->partial, np, roi->n_roi, ncta, roi->ex,
+                                                                         roi->ey, t0 + 1, roi->out, roi->T);
+            LAUNCH_CHECK();
+        }
+        return 0;
+    }
+    for (int i = 0; i < nsc; ++i) {
+        const ScaleInfo& s = p->sc[i];
+        const bool finest = (i == nsc - 1);
+        const size_t m_stride = 5 * s.plane;
+        bf::UpdateArgs u{};
+        u.R = s.R; u.plane_stride = s.plane; u.slot_stride = 5 * s.plane; u.slot0 = slot0; u.nslots = p->F;
+        u.pitch = s.pitch; u.w = s.w; u.h = s.h;
+        if (i == 0) {
+            u.flow_mode = 0;
+        } else {
+            const ScaleInfo& c = p->sc[i - 1];
+            u.flow_mode = 2;
+            u.flow = c.flow; u.flow_pitch = c.pitch; u.flow_stride = c.plane;
+            u.ws = c.w; u.hs = c.h; u.mult = (float)(1.0 / p->prm.pyr_scale);
+            u.tab = bf::ResizeTab{s.fix, s.fax, s.fiy, s.fay};
+        }
+        u.M = p->M[0]; u.m_stride = m_stride;
+        int rc = launch_update(u, np, st);
+        if (rc) return rc;
+        for (int it = 0; it < I; ++it) {
+            const bool last = (it == I - 1);
+            bf::BlurSolveArgs a{};
+            a.M = p->M[it & 1]; a.m_stride = m_stride; a.plane_stride = s.plane; a.pitch = s.pitch; a.w = s.w; a.h = s.h;
+            a.R = s.R; a.slot_stride = 5 * s.plane; a.slot0 = slot0; a.nslots = p->F;
+            if (!last) {
+                a.Mout = p->M[(it + 1) & 1];
+            } else if (!finest) {
+                a.flow = s.flow; a.flow_pitch = s.pitch; a.flow_stride = s.plane;
+            } else {
+                if (flow_out) {
+                    a.flow = (float2*)flow_out; a.flow_pitch = p->W; a.flow_stride = (size_t)p->H * p->W;
+                }
+                if (want_roi) {
+                    a.masks = roi->masks; a.n_roi = roi->n_roi; a.mask_stride = (size_t)p->H * p->W; a.mask_pitch = p->W;
+                    a.axes = p->axes; a.partial = p->partial;
+                }
+            }
+            const bool prof = p->prof_on && finest;
+            if (prof) {
+                if (p->prof_used + 2 > p->prof_ev.size()) {
+                    for (int e = 0; e < 2; ++e) {
+                        cudaEvent_t ev;
+                        CU(cudaEventCreate(&ev));
+                        p->prof_ev.push_back(ev);
+                    }
+                }
+                CU(cudaEventRecord(p->prof_ev[p->prof_used], st));
+            }
+            rc = launch_blur_solve(a, p->wc, np, p->use_fast, st);
+            if (rc) return rc;
+            if (prof) {
+                CU(cudaEventRecord(p->prof_ev[p->prof_used + 1], st));
+                p->prof_used += 2;
+                p->prof_pairs += np;
+            }
+            if (last && finest && want_roi) {
+                const int ncta = blur_solve_ncta(s.w, s.h, p->wc, p->use_fast, s.pitch);
+                bf::k_roi_finalize<<<cdiv(np * roi->n_roi, 64), 64, 0, st>>>(p->partial, np, roi->n_roi, ncta, roi->ex,
+                                                                             roi->ey, t0 + 1, roi->out, roi->T);
+                LAUNCH_CHECK();
+            }
+        }
+    }
+    return 0;
+}
+
+int check_plan(const bf_plan* p) {
+    if (!p) return fail(BF_E_INVALID, "plan is NULL");
+    return 0;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// C-ABI
+// =========================================================================================================
+extern "C" {
+
+const char* bf_last_error(void) { return g_err.c_str(); }
+const char* bf_version(void) { return "btcsflow 0.1 (sm_100a)"; }
+long long bf_launch_count(void) { return g_launches; }
+void bf_launch_count_reset(void) { g_launches = 0; }
+
+int bf_device_sm(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        cudaGetLastError();
+        return fail(BF_E_NODEVICE, "no usable CUDA device %d (this library has no CPU fallback)", device);
+    }
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) return fail(BF_E_NODEVICE, "cudaGetDeviceProperties failed");
+    return pr.major * 10 + pr.minor;
+}
+
+int bf_plan_create(const bf_params* params, int width, int height, int max_pairs, int max_rois, int device,
+                   bf_plan** out) {
+    if (!out) return fail(BF_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = validate_params(params, width, height);
+    if (rc) return rc;
+    if (max_pairs < 1 || max_rois < 0) return fail(BF_E_INVALID, "max_pairs must be >= 1 and max_rois >= 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(BF_E_NODEVICE, "no usable CUDA device %d (this library has no CPU fallback)", device);
+    }
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(BF_E_NODEVICE, "cudaSetDevice(%d) failed", device);
+
+    bf_plan* p = new bf_plan();
+    p->prm = *params;
+    p->W = width; p->H = height; p->B = max_pairs; p->F = max_pairs + 1; p->max_rois = max_rois; p->device = device;
+    if (!make_poly_coef(params->poly_n, params->poly_sigma, p->pc)) {
+        delete p;
+        return fail(BF_E_INVALID, "singular moment matrix for poly_n=%d poly_sigma=%g", params->poly_n, params->poly_sigma);
+    }
+    make_win_coef(params->winsize, params->flags, p->wc);
+
+    // scale selection
+    int k = 0;
+    double scv = 1.0;
+    for (; k < params->levels; ++k) {
+        scv *= params->pyr_scale;
+        if (width * scv < 32 || height * scv < 32) break;
+    }
+    const int L = k;
+    if (L + 1 > BF_MAX_SCALES) { delete p; return fail(BF_E_UNSUPPORTED, "too many scales (%d)", L + 1); }
+    for (int kk = L; kk >= 0; --kk) {
+        ScaleInfo s{};
+        double scale = 1.0;
+        for (int i = 0; i < kk; ++i) scale *= params->pyr_scale;
+        s.k = kk; s.scale = scale;
+        s.sigma = (1.0 / scale - 1.0) * 0.5;
+        s.ksize = std::max(cv_round(s.sigma * 5) | 1, 3);
+        s.w = cv_round(width * scale);
+        s.h = cv_round(height * scale);
+        s.pitch = round_up(s.w, 32);
+        s.plane = (size_t)s.h * s.pitch;
+        p->sc.push_back(s);
+    }
+    auto cleanup_fail = [&](int code) { bf_plan_destroy(p); return code; };
+    for (size_t i = 0; i < p->sc.size(); ++i) {
+        ScaleInfo& s = p->sc[i];
+        std::vector<int> idx; std::vector<float> wgt;
+        resize_table(s.w, width, idx, wgt);
+        if (upload(idx, &s.ix) != cudaSuccess || upload(wgt, &s.ax) != cudaSuccess) return cleanup_fail(fail(2, "table upload failed"));
+        resize_table(s.h, height, idx, wgt);
+        if (upload(idx, &s.iy) != cudaSuccess || upload(wgt, &s.ay) != cudaSuccess) return cleanup_fail(fail(2, "table upload failed"));
+        std::vector<float> kern = gaussian_kernel(s.ksize, s.sigma);
+        if (upload(kern, &s.kern) != cudaSuccess) return cleanup_fail(fail(2, "table upload failed"));
+        if (i > 0) {
+            const ScaleInfo& c = p->sc[i - 1];
+            resize_table(s.w, c.w, idx, wgt);
+            if (upload(idx, &s.fix) != cudaSuccess || upload(wgt, &s.fax) != cudaSuccess) return cleanup_fail(fail(2, "table upload failed"));
+            resize_table(s.h, c.h, idx, wgt);
+            if (upload(idx, &s.fiy) != cudaSuccess || upload(wgt, &s.fay) != cudaSuccess) return cleanup_fail(fail(2, "table upload failed"));
+        }
+        if ((rc = plan_alloc(p, &s.I, (size_t)p->F * s.plane))) return cleanup_fail(rc);
+        if ((rc = plan_alloc(p, &s.R, (size_t)p->F * 5 * s.plane))) return cleanup_fail(rc);
+        if ((rc = plan_alloc(p, &s.flow, (size_t)p->B * s.plane))) return cleanup_fail(rc);
+        // rows [h, pitch) padding must hold finite values for vectorised kernels: zero everything once
+        cudaMemset(s.I, 0, (size_t)p->F * s.plane * sizeof(float));
+        cudaMemset(s.R, 0, (size_t)p->F * 5 * s.plane * sizeof(float));
+        cudaMemset(s.flow, 0, (size_t)p->B * s.plane * sizeof(float2));
+    }
+    const ScaleInfo& fine = p->sc.back();
+    size_t tmp_elems = 0, m_elems = 0;
+    for (auto& s : p->sc) {
+        tmp_elems = std::max(tmp_elems, (size_t)p->F * height * s.pitch);
+        m_elems = std::max(m_elems, (size_t)p->B * 5 * s.plane);
+    }
+    if ((rc = plan_alloc(p, &p->tmp, tmp_elems))) return cleanup_fail(rc);
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = plan_alloc(p, &p->M[i], m_elems))) return cleanup_fail(rc);
+        cudaMemset(p->M[i], 0, m_elems * sizeof(float));
+    }
+    if ((rc = plan_alloc(p, &p->axes, (size_t)p->B * 4))) return cleanup_fail(rc);
+    p->ncta_max = std::max(cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), bf::blur_solve_fast_ncta(fine.w, fine.h));
+    if ((rc = plan_alloc(p, &p->partial, (size_t)p->B * std::max(max_rois, 1) * p->ncta_max * bf::kRoiVals))) return cleanup_fail(rc);
+    const char* nofast = getenv("BTCSFLOW_NO_FAST");
+    p->use_fast = !(nofast && nofast[0] == '1');
+    if (cudaDeviceSynchronize() != cudaSuccess) return cleanup_fail(fail(2, "plan initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = p;
+    return 0;
+}
+
+int bf_plan_destroy(bf_plan* p) {
+    if (!p) return 0;
+    DeviceGuard dg(p->device);
+    for (auto& s : p->sc) {
+        cudaFree(s.ix); cudaFree(s.iy); cudaFree(s.ax); cudaFree(s.ay); cudaFree(s.kern);
+        cudaFree(s.fix); cudaFree(s.fiy); cudaFree(s.fax); cudaFree(s.fay);
+        cudaFree(s.I); cudaFree(s.R); cudaFree(s.flow);
+    }
+    cudaFree(p->tmp); cudaFree(p->M[0]); cudaFree(p->M[1]); cudaFree(p->axes); cudaFree(p->partial);
+    cudaFree(p->stage[0]); cudaFree(p->stage[1]); cudaFree(p->stage_flow);
+    cudaFree(p->d_ex); cudaFree(p->d_ey); cudaFree(p->d_masks); cudaFree(p->d_out);
+    for (int i = 0; i < 2; ++i) {
+        if (p->ev_copied[i]) cudaEventDestroy(p->ev_copied[i]);
+        if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]);
+    }
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    for (auto ev : p->prof_ev) cudaEventDestroy(ev);
+    delete p;
+    return 0;
+}
+
+int bf_plan_profile(bf_plan* p, int enable) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    p->prof_on = enable != 0;
+    return 0;
+}
+
+int bf_plan_profile_read(bf_plan* p, int* n_launches, double* total_ms, long long* pair_iterations) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    DeviceGuard dg(p->device);
+    double tot = 0;
+    for (size_t i = 0; i + 1 < p->prof_used; i += 2) {
+        CU(cudaEventSynchronize(p->prof_ev[i + 1]));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, p->prof_ev[i], p->prof_ev[i + 1]));
+        tot += ms;
+    }
+    if (n_launches) *n_launches = (int)(p->prof_used / 2);
+    if (total_ms) *total_ms = tot;
+    if (pair_iterations) *pair_iterations = p->prof_pairs;
+    p->prof_used = 0;
+    p->prof_pairs = 0;
+    return 0;
+}
+
+size_t bf_plan_workspace_bytes(const bf_plan* p) { return p ? p->bytes : 0; }
+int bf_plan_num_scales(const bf_plan* p) { return p ? (int)p->sc.size() : BF_E_INVALID; }
+
+int bf_plan_scale_info(const bf_plan* p, int i, int* w, int* h, int* ksize, double* sigma, int* pitch) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    if (i < 0 || i >= (int)p->sc.size()) return fail(BF_E_INVALID, "scale index %d out of range", i);
+    const ScaleInfo& s = p->sc[i];
+    if (w) *w = s.w;
+    if (h) *h = s.h;
+    if (ksize) *ksize = s.ksize;
+    if (sigma) *sigma = s.sigma;
+    if (pitch) *pitch = s.pitch;
+    return 0;
+}
+
+int bf_flow_pair(bf_plan* p, const void* prev, const void* next, int dtype, size_t pitch_bytes, float* flow_out,
+                 void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    if (!prev || !next || !flow_out) return fail(BF_E_INVALID, "NULL image/flow pointer");
+    if (dtype != BF_DTYPE_U8 && dtype != BF_DTYPE_F32) return fail(BF_E_INVALID, "dtype must be BF_DTYPE_U8 or BF_DTYPE_F32");
+    const size_t esz = dtype == BF_DTYPE_U8 ? 1 : 4;
+    if (pitch_bytes < (size_t)p->W * esz) return fail(BF_E_INVALID, "pitch_bytes smaller than a row");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const void* fr[2] = {prev, next};
+    for (int i = 0; i < 2; ++i) {
+        if (dtype == BF_DTYPE_U8) rc = expand_frames<uint8_t>(p, (const uint8_t*)fr[i], pitch_bytes, 0, i, 1, st);
+        else rc = expand_frames<float>(p, (const float*)fr[i], pitch_bytes, 0, i, 1, st);
+        if (rc) return rc;
+    }
+    return run_pairs(p, 0, 1, flow_out, nullptr, st);
+}
+
+int bf_flow_pair_host(bf_plan* p, const void* prev, const void* next, int dtype, size_t pitch_bytes, float* flow_out,
+                      void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    if (!prev || !next || !flow_out) return fail(BF_E_INVALID, "NULL image/flow pointer");
+    if (dtype != BF_DTYPE_U8 && dtype != BF_DTYPE_F32) return fail(BF_E_INVALID, "dtype must be BF_DTYPE_U8 or BF_DTYPE_F32");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t img_bytes = pitch_bytes * p->H;
+    const size_t flow_bytes = (size_t)p->H * p->W * sizeof(float2);
+    void *d0 = nullptr, *d1 = nullptr, *df = nullptr;
+    CU(cudaMallocAsync(&d0, img_bytes, st));
+    CU(cudaMallocAsync(&d1, img_bytes, st));
+    CU(cudaMallocAsync(&df, flow_bytes, st));
+    CU(cudaMemcpyAsync(d0, prev, img_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d1, next, img_bytes, cudaMemcpyHostToDevice, st));
+    rc = bf_flow_pair(p, d0, d1, dtype, pitch_bytes, (float*)df, stream);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(flow_out, df, flow_bytes, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = fail((int)e, "D2H copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFreeAsync(d0, st); cudaFreeAsync(d1, st); cudaFreeAsync(df, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = fail((int)e, "stream sync failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+int bf_flow_series(bf_plan* p, const uint8_t* frames, int T, const double* ex, const double* ey,
+                   const uint8_t* roi_masks, int n_roi, float* out, float* flow_out, void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    if (T < 1 || !frames) return fail(BF_E_INVALID, "need frames and T >= 1");
+    if (n_roi < 0 || n_roi > p->max_rois) return fail(BF_E_INVALID, "n_roi=%d exceeds plan max_rois=%d", n_roi, p->max_rois);
+    if (n_roi > 0 && (!roi_masks || !out || !ex || !ey)) return fail(BF_E_INVALID, "ROI reduction needs masks, axes and out");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t fb = (size_t)p->H * p->W;
+    if (n_roi > 0) {
+        const int n = n_roi * T * 3;
+        bf::k_fill_nan<<<cdiv(n, 256), 256, 0, st>>>(out, n);
+        LAUNCH_CHECK();
+    }
+    RoiCtx roi;
+    roi.masks = roi_masks; roi.n_roi = n_roi; roi.ex = ex; roi.ey = ey; roi.out = out; roi.T = T;
+    for (int t0 = 0; t0 < T - 1; t0 += p->B) {
+        const int np = std::min(p->B, T - 1 - t0);
+        const int tf = (t0 == 0) ? 0 : t0 + 1;  // frame t0 of a later batch is already expanded (ring)
+        const int nf = t0 + np - tf + 1;
+        rc = expand_frames<uint8_t>(p, frames + (size_t)tf * fb, (size_t)p->W, fb, tf, nf, st);
+        if (rc) return rc;
+        rc = run_pairs(p, t0, np, flow_out ? flow_out + (size_t)t0 * fb * 2 : nullptr, n_roi > 0 ? &roi : nullptr, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* ex, const double* ey,
+                        const uint8_t* roi_masks, int n_roi, float* out, float* flow_out, void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    if (T < 1 || !frames) return fail(BF_E_INVALID, "need frames and T >= 1");
+    if (n_roi < 0 || n_roi > p->max_rois) return fail(BF_E_INVALID, "n_roi=%d exceeds plan max_rois=%d", n_roi, p->max_rois);
+    if (n_roi > 0 && (!roi_masks || !out || !ex || !ey)) return fail(BF_E_INVALID, "ROI reduction needs masks, axes and out");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t fb = (size_t)p->H * p->W;
+    // lazily created staging resources
+    if (!p->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&p->ev_copied[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_free[i], cudaEventDisableTiming));
+            if ((rc = plan_alloc(p, &p->stage[i], (size_t)p->F * fb))) return rc;
+        }
+    }
+    if (flow_out && !p->stage_flow) {
+        if ((rc = plan_alloc(p, &p->stage_flow, (size_t)p->B * fb * 2))) return rc;
+    }
+    RoiCtx roi;
+    if (n_roi > 0) {
+        if (p->axes_cap < T) {
+            cudaFree(p->d_ex); cudaFree(p->d_ey); p->d_ex = p->d_ey = nullptr;
+            CU(cudaMalloc((void**)&p->d_ex, (size_t)T * 2 * sizeof(double)));
+            CU(cudaMalloc((void**)&p->d_ey, (size_t)T * 2 * sizeof(double)));
+            p->axes_cap = T;
+        }
+        const size_t mb = (size_t)n_roi * fb;
+        if (p->masks_cap < mb) {
+            cudaFree(p->d_masks); p->d_masks = nullptr;
+            CU(cudaMalloc((void**)&p->d_masks, mb));
+            p->masks_cap = mb;
+        }
+        const size_t ob = (size_t)n_roi * T * 3;
+        if (p->out_cap < ob) {
+            cudaFree(p->d_out); p->d_out = nullptr;
+            CU(cudaMalloc((void**)&p->d_out, ob * sizeof(float)));
+            p->out_cap = ob;
+        }
+        CU(cudaMemcpyAsync(p->d_ex, ex, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(p->d_ey, ey, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(p->d_masks, roi_masks, mb, cudaMemcpyHostToDevice, st));
+        const int n = (int)ob;
+        bf::k_fill_nan<<<cdiv(n, 256), 256, 0, st>>>(p->d_out, n);
+        LAUNCH_CHECK();
+        roi.masks = p->d_masks; roi.n_roi = n_roi; roi.ex = p->d_ex; roi.ey = p->d_ey; roi.out = p->d_out; roi.T = T;
+    }
+    // the copy stream must not overwrite a staging buffer a previous call on `st` may still be reading
+    int chunk = 0;
+    for (int t0 = 0; t0 < T - 1; t0 += p->B, ++chunk) {
+        const int np = std::min(p->B, T - 1 - t0);
+        const int tf = (t0 == 0) ? 0 : t0 + 1;
+        const int nf = t0 + np - tf + 1;
+        const int b = chunk & 1;
+        if (chunk >= 2) CU(cudaStreamWaitEvent(p->copy_stream, p->ev_free[b], 0));
+        CU(cudaMemcpyAsync(p->stage[b], frames + (size_t)tf * fb, (size_t)nf * fb, cudaMemcpyHostToDevice, p->copy_stream));
+        CU(cudaEventRecord(p->ev_copied[b], p->copy_stream));
+        CU(cudaStreamWaitEvent(st, p->ev_copied[b], 0));
+        rc = expand_frames<uint8_t>(p, p->stage[b], (size_t)p->W, fb, tf, nf, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(p->ev_free[b], st));
+        rc = run_pairs(p, t0, np, flow_out ? p->stage_flow : nullptr, n_roi > 0 ? &roi : nullptr, st);
+        if (rc) return rc;
+        if (flow_out)
+            CU(cudaMemcpyAsync(flow_out + (size_t)t0 * fb * 2, p->stage_flow, (size_t)np * fb * 2 * sizeof(float),
+                               cudaMemcpyDeviceToHost, st));
+    }
+    if (n_roi > 0)
+        CU(cudaMemcpyAsync(out, p->d_out, (size_t)n_roi * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(p->copy_stream));
+    return 0;
+}
+
+// ---- PC1 ------------------------------------------------------------------------------------------------
+
+int bf_pc1_sliding_batched(const double* vx, const double* vy, int n_series, int n, const int* win_n,
+                           const int* step_n, int n_cfg, double ref_x, double ref_y, int min_samples,
+                           double* pc1_out, void* stream) {
+    if (!vx || !vy || !pc1_out || !win_n || !step_n) return fail(BF_E_INVALID, "NULL pointer");
+    if (n_series < 1 || n < 0 || n_cfg < 1) return fail(BF_E_INVALID, "bad sizes");
+    if (min_samples < 1) return fail(BF_E_INVALID, "min_samples must be >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return 0;
+    std::vector<bf::Pc1Cfg> cfgs(n_cfg);
+    int Ktot = 0, Kmax = 0;
+    for (int c = 0; c < n_cfg; ++c) {
+        if (win_n[c] < 1 || step_n[c] < 1) return fail(BF_E_INVALID, "win_n and step_n must be >= 1");
+        // optical_PCA.py:171-172,181: fewer than MIN_SAMPLES samples, or n < win_n -> no windows -> all NaN
+        int K = 0;
+        if (n >= min_samples && n >= win_n[c]) K = (n - win_n[c]) / step_n[c] + 1;
+        cfgs[c] = bf::Pc1Cfg{win_n[c], step_n[c], K, Ktot};
+        Ktot += K;
+        Kmax = std::max(Kmax, K);
+    }
+    const size_t nw = (size_t)n_series * std::max(Ktot, 1);
+    bf::Pc1Cfg* d_cfg = nullptr;
+    double* d_w = nullptr;  // wx, wy, cwx, cwy
+    int* d_i = nullptr;     // valid, cen, nvalid
+    CU(cudaMallocAsync((void**)&d_cfg, n_cfg * sizeof(bf::Pc1Cfg), st));
+    CU(cudaMallocAsync((void**)&d_w, 4 * nw * sizeof(double), st));
+    CU(cudaMallocAsync((void**)&d_i, (2 * nw + (size_t)n_series * n_cfg) * sizeof(int), st));
+    // pageable source: the copy is staged before the call returns, so the vector may die afterwards
+    CU(cudaMemcpyAsync(d_cfg, cfgs.data(), n_cfg * sizeof(bf::Pc1Cfg), cudaMemcpyHostToDevice, st));
+    double *wx = d_w, *wy = d_w + nw, *cwx = d_w + 2 * nw, *cwy = d_w + 3 * nw;
+    int *valid = d_i, *cen = d_i + nw, *nvalid = d_i + 2 * nw;
+    if (Kmax > 0) {
+        dim3 gA(cdiv(Kmax, 128), n_series, n_cfg);
+        bf::k_pc1_windows<<<gA, 128, 0, st>>>(vx, vy, n_series, n, d_cfg, n_cfg, Ktot, ref_x, ref_y, min_samples, wx, wy, valid);
+        LAUNCH_CHECK();
+    }
+    dim3 gB(n_series, n_cfg);
+    bf::k_pc1_chain<<<gB, 1024, 1024 * sizeof(int), st>>>(d_cfg, n_cfg, Ktot, wx, wy, valid, cwx, cwy, cen, nvalid);
+    LAUNCH_CHECK();
+    dim3 gC(cdiv(n, 256), n_series, n_cfg);
+    bf::k_pc1_project<<<gC, 256, 0, st>>>(vx, vy, n_series, n, d_cfg, n_cfg, Ktot, cwx, cwy, cen, nvalid, pc1_out);
+    LAUNCH_CHECK();
+    CU(cudaFreeAsync(d_cfg, st));
+    CU(cudaFreeAsync(d_w, st));
+    CU(cudaFreeAsync(d_i, st));
+    return 0;
+}
+
+int bf_pc1_sliding(const double* vx, const double* vy, int n, int win_n, int step_n, double ref_x, double ref_y,
+                   int min_samples, double* pc1_out, void* stream) {
+    return bf_pc1_sliding_batched(vx, vy, 1, n, &win_n, &step_n, 1, ref_x, ref_y, min_samples, pc1_out, stream);
+}
+
+int bf_pc1_sliding_host(const double* vx, const double* vy, int n, int win_n, int step_n, double ref_x, double ref_y,
+                        int min_samples, double* pc1_out) {
+    if (!vx || !vy || !pc1_out) return fail(BF_E_INVALID, "NULL pointer");
+    if (n <= 0) return n == 0 ? 0 : fail(BF_E_INVALID, "n < 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(BF_E_NODEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    }
+    double* d = nullptr;
+    CU(cudaMalloc((void**)&d, (size_t)3 * n * sizeof(double)));
+    int rc = 0;
+    cudaError_t e = cudaMemcpy(d, vx, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + n, vy, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = fail((int)e, "H2D failed: %s", cudaGetErrorString(e));
+    if (!rc) rc = bf_pc1_sliding(d, d + n, n, win_n, step_n, ref_x, ref_y, min_samples, d + 2 * n, nullptr);
+    if (!rc) {
+        e = cudaMemcpy(pc1_out, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail((int)e, "D2H failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+// ---- stage-level entry points ---------------------------------------------------------------------------
+
+int bf_stage_level_image(bf_plan* p, const void* frame, int dtype, size_t pitch_bytes, int scale_index, float* out,
+                         void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    if (!frame || !out) return fail(BF_E_INVALID, "NULL pointer");
+    if (scale_index < 0 || scale_index >= (int)p->sc.size()) return fail(BF_E_INVALID, "scale index out of range");
+    DeviceGuard dg(p->device);
+    const ScaleInfo& s = p->sc[scale_index];
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == BF_DTYPE_U8) return launch_pyramid<uint8_t>(p, s, (const uint8_t*)frame, pitch_bytes, 0, 1, out, s.w, (size_t)s.w * s.h, st);
+    if (dtype == BF_DTYPE_F32) return launch_pyramid<float>(p, s, (const float*)frame, pitch_bytes, 0, 1, out, s.w, (size_t)s.w * s.h, st);
+    return fail(BF_E_INVALID, "bad dtype");
+}
+
+int bf_stage_poly_exp(const float* image, int w, int h, int poly_n, double poly_sigma, float* R_planes, void* stream) {
+    if (!image || !R_planes || w <= 0 || h <= 0) return fail(BF_E_INVALID, "bad arguments");
+    if (poly_n < 1 || poly_n > BF_MAX_POLY_N) return fail(BF_E_UNSUPPORTED, "poly_n out of range");
+    bf::PolyCoef pc;
+    if (!make_poly_coef(poly_n, poly_sigma, pc)) return fail(BF_E_INVALID, "singular moment matrix");
+    const char* nofast = getenv("BTCSFLOW_NO_FAST");
+    const bool fast = !(nofast && nofast[0] == '1');
+    return launch_polyexp(nullptr, image, w, (size_t)w * h, w, h, R_planes, (size_t)w * h, (size_t)5 * w * h, 0, 1, 1, pc,
+                          fast, (cudaStream_t)stream);
+}
+
+int bf_stage_update_matrices(const float* R0, const float* R1, const float* flow, int w, int h, float* M, void* stream) {
+    if (!R0 || !R1 || !flow || !M || w <= 0 || h <= 0) return fail(BF_E_INVALID, "bad arguments");
+    // R0 and R1 are separate allocations: express R1 as "slot 1" relative to R0 only when contiguous;
+    // otherwise run with a two-slot view through pointer difference (must be a multiple of a float).
+    const size_t plane = (size_t)w * h;
+    bf::UpdateArgs u{};
+    const ptrdiff_t diff = R1 - R0;
+    u.R = R0; u.plane_stride = plane; u.slot_stride = (size_t)diff; u.slot0 = 0; u.nslots = 2;
+    u.pitch = w; u.w = w; u.h = h;
+    u.flow_mode = 1; u.flow = (const float2*)flow; u.flow_pitch = w; u.flow_stride = 0;
+    u.M = M; u.m_stride = 0;
+    return launch_update(u, 1, (cudaStream_t)stream);
+}
+
+int bf_stage_blur_solve(const float* M, int w, int h, int winsize, int flags, float* flow, void* stream) {
+    if (!M || !flow || w <= 0 || h <= 0 || winsize < 1) return fail(BF_E_INVALID, "bad arguments");
+    if (winsize / 2 > BF_MAX_WIN_HALF) return fail(BF_E_UNSUPPORTED, "winsize too large");
+    bf::WinCoef wc;
+    make_win_coef(winsize, flags, wc);
+    bf::BlurSolveArgs a{};
+    a.M = M; a.m_stride = 0; a.plane_stride = (size_t)w * h; a.pitch = w; a.w = w; a.h = h;
+    a.flow = (float2*)flow; a.flow_pitch = w; a.flow_stride = 0;
+    const char* nofast = getenv("BTCSFLOW_NO_FAST");
+    const bool fast = !(nofast && nofast[0] == '1');
+    return launch_blur_solve(a, wc, 1, fast, (cudaStream_t)stream);
+}
+
+int bf_stage_upsample_flow(const float* flow_in, int ws, int hs, int w, int h, float mult, float* flow_out, void* stream) {
+    if (!flow_in || !flow_out || ws <= 0 || hs <= 0 || w <= 0 || h <= 0) return fail(BF_E_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int> ix, iy; std::vector<float> ax, ay;
+    resize_table(w, ws, ix, ax);
+    resize_table(h, hs, iy, ay);
+    int *dix = nullptr, *diy = nullptr; float *dax = nullptr, *day = nullptr;
+    CU(cudaMallocAsync((void**)&dix, w * sizeof(int), st));
+    CU(cudaMallocAsync((void**)&diy, h * sizeof(int), st));
+    CU(cudaMallocAsync((void**)&dax, w * sizeof(float), st));
+    CU(cudaMallocAsync((void**)&day, h * sizeof(float), st));
+    CU(cudaMemcpyAsync(dix, ix.data(), w * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(diy, iy.data(), h * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dax, ax.data(), w * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(day, ay.data(), h * sizeof(float), cudaMemcpyHostToDevice, st));
+    bf::UpdateArgs u{};
+    u.w = w; u.h = h; u.flow_mode = 2;
+    u.flow = (const float2*)flow_in; u.flow_pitch = ws; u.flow_stride = 0; u.ws = ws; u.hs = hs; u.mult = mult;
+    u.tab = bf::ResizeTab{dix, dax, diy, day};
+    u.flow_out = (float2*)flow_out; u.flow_out_pitch = w; u.flow_out_stride = 0;
+    int rc = launch_update(u, 1, st);
+    cudaFreeAsync(dix, st); cudaFreeAsync(diy, st); cudaFreeAsync(dax, st); cudaFreeAsync(day, st);
+    CU(cudaStreamSynchronize(st));  // the host tables above must outlive the async copies
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,506 @@
+// Farneback dense optical flow: generic (runtime-parameter) CUDA kernels for sm_100a.
+//
+// Algorithm restated from the validated behavioural spec of cv2.calcOpticalFlowFarneback (the single
+// hot call of the reference, /root/reference/optical_flow.py:173; spec in SURVEY.md Appendix A).
+// Data layout in HBM (all float32 unless noted):
+//   level image  I   [frame][h][pitch]
+//   poly coeffs  R   [slot][5][h][pitch]   planes (b_y, b_x, A_yy, A_xx, A_xy)      -- SoA so that both the
+//   matrices     M   [pair][5][h][pitch]   planes (G11, G12, G22, h1, h2)              pointwise reads and the
+//   flow             [pair][h][pitch] float2 (dx, dy)                                  bilinear gather coalesce
+// `pitch` is in elements and a multiple of 32 for plan-owned buffers (128-byte rows).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bf {
+
+constexpr int kMaxPolyN = 16;
+constexpr int kMaxWinHalf = 64;
+
+struct PolyCoef {
+    float g[kMaxPolyN + 1];
+    float xg[kMaxPolyN + 1];
+    float xxg[kMaxPolyN + 1];
+    float ig11, ig03, ig33, ig55;
+    int n;
+};
+
+struct WinCoef {
+    float ker[kMaxWinHalf + 1];  // Gaussian window taps ker[0..m] (normalised); unused for box
+    float scale;                 // box: 1 / winsize^2 ; Gaussian: 1
+    int m;                       // half window
+    int gauss;
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        if (i >= n) i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+__device__ __forceinline__ float load_px(const uint8_t* p) { return (float)(*p); }
+__device__ __forceinline__ float load_px(const float* p) { return *p; }
+
+// ---------------------------------------------------------------------------------------------------
+// K1a: horizontal part of (GaussianBlur REFLECT_101 -> bilinear resize), evaluated only at the columns
+// the resize samples.  tmp[f][r][x] for every source row r.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pyr_h(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes, int W, int H,
+                        int w, const int* __restrict__ ix, const float* __restrict__ ax,
+                        const float* __restrict__ kern, int ksize, float* __restrict__ tmp, int tmp_pitch,
+                        size_t tmp_frame_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.z;
+    if (x >= w || r >= H) return;
+    const T* row = (const T*)((const char*)src + (size_t)f * src_frame_bytes + (size_t)r * src_pitch_bytes);
+    const int rad = ksize >> 1;
+    const int i0 = ix[x];
+    const float a = ax[x];
+    float b0 = 0.f, b1 = 0.f;
+    if (i0 - rad >= 0 && i0 + 1 + rad < W) {
+        // interior: share the overlapping taps of the two neighbouring blurred samples
+        float prev = load_px(row + i0 - rad);
+        for (int j = 0; j < ksize; ++j) {
+            const float nxt = load_px(row + i0 - rad + j + 1);
+            const float kj = __ldg(kern + j);
+            b0 = fmaf(kj, prev, b0);
+            b1 = fmaf(kj, nxt, b1);
+            prev = nxt;
+        }
+    } else {
+        for (int j = 0; j < ksize; ++j) {
+            const float kj = __ldg(kern + j);
+            b0 = fmaf(kj, load_px(row + reflect101(i0 - rad + j, W)), b0);
+        }
+        if (a != 0.f) {
+            const int i1 = min(i0 + 1, W - 1);
+            for (int j = 0; j < ksize; ++j)
+                b1 = fmaf(__ldg(kern + j), load_px(row + reflect101(i1 - rad + j, W)), b1);
+        }
+    }
+    const float v = (a != 0.f) ? (b0 * (1.f - a) + b1 * a) : b0;
+    tmp[(size_t)f * tmp_frame_stride + (size_t)r * tmp_pitch + x] = v;
+}
+
+// K1b: vertical part; out[f][y][x] = lerp_y( blur_v(tmp) ).
+__global__ void k_pyr_v(const float* __restrict__ tmp, int tmp_pitch, size_t tmp_frame_stride, int H, int w,
+                        int h, const int* __restrict__ iy, const float* __restrict__ ay,
+                        const float* __restrict__ kern, int ksize, float* __restrict__ out, int out_pitch,
+                        size_t out_frame_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.z;
+    if (x >= w || y >= h) return;
+    const float* t = tmp + (size_t)f * tmp_frame_stride + x;
+    const int rad = ksize >> 1;
+    const int i0 = iy[y];
+    const float a = ay[y];
+    float b0 = 0.f, b1 = 0.f;
+    if (i0 - rad >= 0 && i0 + 1 + rad < H) {
+        float prev = t[(size_t)(i0 - rad) * tmp_pitch];
+        for (int j = 0; j < ksize; ++j) {
+            const float nxt = t[(size_t)(i0 - rad + j + 1) * tmp_pitch];
+            const float kj = __ldg(kern + j);
+            b0 = fmaf(kj, prev, b0);
+            b1 = fmaf(kj, nxt, b1);
+            prev = nxt;
+        }
+    } else {
+        for (int j = 0; j < ksize; ++j)
+            b0 = fmaf(__ldg(kern + j), t[(size_t)reflect101(i0 - rad + j, H) * tmp_pitch], b0);
+        if (a != 0.f) {
+            const int i1 = min(i0 + 1, H - 1);
+            for (int j = 0; j < ksize; ++j)
+                b1 = fmaf(__ldg(kern + j), t[(size_t)reflect101(i1 - rad + j, H) * tmp_pitch], b1);
+        }
+    }
+    const float v = (a != 0.f) ? (b0 * (1.f - a) + b1 * a) : b0;
+    out[(size_t)f * out_frame_stride + (size_t)y * out_pitch + x] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2 (generic): separable polynomial expansion.  Tile 64 x 16, 256 threads.
+// Vertical pass straight from global (rows clamped = replicate), horizontal pass from shared memory
+// (columns clamped = replicate of the vertical-pass result, exactly as cv2 pads its row buffer).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPeTW = 64, kPeTH = 16;
+
+__global__ void __launch_bounds__(256) k_polyexp_generic(const float* __restrict__ I, int pitch,
+                                                         size_t frame_stride, int w, int h,
+                                                         float* __restrict__ R, size_t plane_stride,
+                                                         size_t slot_stride, int slot0, int nslots,
+                                                         const PolyCoef pc) {
+    __shared__ float s[3][kPeTH][kPeTW + 2 * kMaxPolyN];
+    const int n = pc.n;
+    const int x0 = blockIdx.x * kPeTW, y0 = blockIdx.y * kPeTH;
+    const int f = blockIdx.z;
+    const float* img = I + (size_t)f * frame_stride;
+    const int tw = kPeTW + 2 * n;
+    for (int it = threadIdx.x; it < kPeTH * tw; it += blockDim.x) {
+        const int ty = it / tw, tx = it - ty * tw;
+        const int gy = y0 + ty;
+        if (gy >= h) continue;
+        const int gx = min(max(x0 - n + tx, 0), w - 1);
+        const float c = img[(size_t)gy * pitch + gx];
+        float t0 = c * pc.g[0], t1 = 0.f, t2 = 0.f;
+        for (int k = 1; k <= n; ++k) {
+            const float up = img[(size_t)max(gy - k, 0) * pitch + gx];
+            const float dn = img[(size_t)min(gy + k, h - 1) * pitch + gx];
+            const float p = up + dn;
+            t0 = fmaf(pc.g[k], p, t0);
+            t1 = fmaf(pc.xg[k], dn - up, t1);
+            t2 = fmaf(pc.xxg[k], p, t2);
+        }
+        s[0][ty][tx] = t0;
+        s[1][ty][tx] = t1;
+        s[2][ty][tx] = t2;
+    }
+    __syncthreads();
+    float* Rb = R + (size_t)((slot0 + f) % nslots) * slot_stride;
+    for (int it = threadIdx.x; it < kPeTH * kPeTW; it += blockDim.x) {
+        const int ty = it / kPeTW, tx = it - ty * kPeTW;
+        const int gx = x0 + tx, gy = y0 + ty;
+        if (gx >= w || gy >= h) continue;
+        const int cx = tx + n;
+        float b1 = s[0][ty][cx] * pc.g[0], b3 = s[1][ty][cx] * pc.g[0], b5 = s[2][ty][cx] * pc.g[0];
+        float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+        for (int k = 1; k <= n; ++k) {
+            const float p0 = s[0][ty][cx + k], m0 = s[0][ty][cx - k];
+            const float p1 = s[1][ty][cx + k], m1 = s[1][ty][cx - k];
+            const float p2 = s[2][ty][cx + k], m2 = s[2][ty][cx - k];
+            const float tg = p0 + m0;
+            b1 = fmaf(tg, pc.g[k], b1);
+            b4 = fmaf(tg, pc.xxg[k], b4);
+            b2 = fmaf(p0 - m0, pc.xg[k], b2);
+            b3 = fmaf(p1 + m1, pc.g[k], b3);
+            b6 = fmaf(p1 - m1, pc.xg[k], b6);
+            b5 = fmaf(p2 + m2, pc.g[k], b5);
+        }
+        const size_t o = (size_t)gy * pitch + gx;
+        Rb[o] = b3 * pc.ig11;
+        Rb[plane_stride + o] = b2 * pc.ig11;
+        Rb[2 * plane_stride + o] = fmaf(b1, pc.ig03, b5 * pc.ig33);
+        Rb[3 * plane_stride + o] = fmaf(b1, pc.ig03, b4 * pc.ig33);
+        Rb[4 * plane_stride + o] = b6 * pc.ig55;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// UpdateMatrices for one pixel: bilinear gather of R1 at (x+dx, y+dy), fallback branch when
+// the 2x2 footprint is not strictly inside, border attenuation in the outer 5 px.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float border_w(int i, int n) {
+    // table {0.14, 0.14, 0.4472, 0.4472, 0.4472}
+    float s = 1.f;
+    if (i < 5) s *= (i < 2) ? 0.14f : 0.4472f;
+    const int j = n - 1 - i;
+    if (j < 5) s *= (j < 2) ? 0.14f : 0.4472f;
+    return s;
+}
+
+__device__ __forceinline__ void update_px(const float* __restrict__ R0, const float* __restrict__ R1,
+                                          size_t plane_stride, int pitch, int w, int h, int x, int y,
+                                          float dx, float dy, float out[5]) {
+    const size_t o = (size_t)y * pitch + x;
+    float fx = (float)x + dx, fy = (float)y + dy;
+    const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+    fx -= (float)x1;
+    fy -= (float)y1;
+    float r2, r3, r4, r5, r6;
+    const float q0 = R0[o], q1 = R0[plane_stride + o], q2 = R0[2 * plane_stride + o],
+                q3 = R0[3 * plane_stride + o], q4 = R0[4 * plane_stride + o];
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const float* p = R1 + (size_t)y1 * pitch + x1;
+        float rw[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float* pc = p + c * plane_stride;
+            rw[c] = a00 * pc[0] + a01 * pc[1] + a10 * pc[pitch] + a11 * pc[pitch + 1];
+        }
+        r2 = rw[0];
+        r3 = rw[1];
+        r4 = (q2 + rw[2]) * 0.5f;
+        r5 = (q3 + rw[3]) * 0.5f;
+        r6 = (q4 + rw[4]) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = q2;
+        r5 = q3;
+        r6 = q4 * 0.5f;
+    }
+    r2 = (q0 - r2) * 0.5f;
+    r3 = (q1 - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float sc = border_w(x, w) * border_w(y, h);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    out[0] = r4 * r4 + r6 * r6;
+    out[1] = (r4 + r5) * r6;
+    out[2] = r5 * r5 + r6 * r6;
+    out[3] = r4 * r2 + r6 * r3;
+    out[4] = r6 * r2 + r5 * r3;
+}
+
+struct ResizeTab {
+    const int* ix; const float* ax;  // [w]
+    const int* iy; const float* ay;  // [h]
+};
+
+// bilinear sample of the coarser flow (cv2.resize INTER_LINEAR, 2 channels) times mult
+__device__ __forceinline__ float2 upsample_flow_px(const float2* __restrict__ fc, int pitch_c, int ws, int hs,
+                                                   const ResizeTab& t, int x, int y, float mult) {
+    const int x0 = t.ix[x], y0 = t.iy[y];
+    const float a = t.ax[x], b = t.ay[y];
+    const int x1 = min(x0 + 1, ws - 1), y1 = min(y0 + 1, hs - 1);
+    const float2 p00 = fc[(size_t)y0 * pitch_c + x0], p01 = fc[(size_t)y0 * pitch_c + x1];
+    const float2 p10 = fc[(size_t)y1 * pitch_c + x0], p11 = fc[(size_t)y1 * pitch_c + x1];
+    const float h0x = p00.x * (1.f - a) + p01.x * a, h0y = p00.y * (1.f - a) + p01.y * a;
+    const float h1x = p10.x * (1.f - a) + p11.x * a, h1y = p10.y * (1.f - a) + p11.y * a;
+    float2 r;
+    r.x = (h0x * (1.f - b) + h1x * b) * mult;
+    r.y = (h0y * (1.f - b) + h1y * b) * mult;
+    return r;
+}
+
+// K3a: M = UpdateMatrices(R0, R1, flow_init).  flow_mode: 0 = zero, 1 = flow buffer, 2 = upsample coarse.
+struct UpdateArgs {
+    const float* R; size_t plane_stride, slot_stride; int slot0, nslots;  // R0 = slot (slot0+p), R1 = next
+    int pitch, w, h;
+    int flow_mode;
+    const float2* flow; int flow_pitch; size_t flow_stride;              // mode 1: [pair][h][flow_pitch]; mode 2: coarse
+    int ws, hs; float mult; ResizeTab tab;
+    float* M; size_t m_stride;                                             // [pair][5][h][pitch]
+    float2* flow_out; int flow_out_pitch; size_t flow_out_stride;          // optional: write flow_init
+};
+
+__global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int p = blockIdx.z;
+    if (x >= a.w || y >= a.h) return;
+    float2 fl = make_float2(0.f, 0.f);
+    if (a.flow_mode == 1) fl = a.flow[(size_t)p * a.flow_stride + (size_t)y * a.flow_pitch + x];
+    else if (a.flow_mode == 2)
+        fl = upsample_flow_px(a.flow + (size_t)p * a.flow_stride, a.flow_pitch, a.ws, a.hs, a.tab, x, y, a.mult);
+    if (a.flow_out) a.flow_out[(size_t)p * a.flow_out_stride + (size_t)y * a.flow_out_pitch + x] = fl;
+    if (!a.M) return;
+    const float* R0 = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
+    const float* R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
+    float m[5];
+    update_px(R0, R1, a.plane_stride, a.pitch, a.w, a.h, x, y, fl.x, fl.y, m);
+    float* M = a.M + (size_t)p * a.m_stride + (size_t)y * a.pitch + x;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) M[c * a.plane_stride] = m[c];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3b (generic): flow = Solve(Blur(M)) [+ M' = UpdateMatrices(flow)] [+ projection and ROI sums].
+// Tile 32 x 8 outputs, 256 threads.  Phase 1: vertical window sums global -> shared (one thread per
+// (channel, column), exact first window then short-history sliding: no long-range cancellation).
+// Phase 2: horizontal sums from shared, accurate 2x2 solve.  Phase 3: fused tail.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBsTW = 32, kBsTH = 8;
+constexpr int kRoiVals = 4;  // sum vx, sum vy, sum mag, count
+
+struct BlurSolveArgs {
+    const float* M; size_t m_stride, plane_stride; int pitch, w, h;
+    // outputs (each optional)
+    float2* flow; int flow_pitch; size_t flow_stride;
+    float* Mout;
+    const float* R; size_t slot_stride; int slot0, nslots;  // for Mout
+    // ROI reduction (optional): masks [n_roi][h][w] u8; axes per pair; partial [pair][roi][ncta][4]
+    const uint8_t* masks; int n_roi; size_t mask_stride; int mask_pitch;
+    const float* axes;  // [pair][4] = ex0, ex1, ey0, ey1
+    float* partial;
+};
+
+// accurate a*b - c*d (Kahan): the structure-tensor determinant cancels heavily where the window holds
+// 1-D structure; cv2 does this solve in double.
+__device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
+    const float cd = c * d;
+    const float err = fmaf(-c, d, cd);
+    const float dop = fmaf(a, b, -cd);
+    return dop + err;
+}
+
+__device__ __forceinline__ float2 solve2x2(float g11, float g12, float g22, float h1, float h2) {
+    const float det = diff_of_products(g11, g22, g12, g12) + 1e-3f;
+    const float idet = 1.f / det;
+    float2 r;
+    r.x = diff_of_products(g11, h2, g12, h1) * idet;
+    r.y = diff_of_products(g22, h1, g12, h2) * idet;
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide ROI partial sums for one pixel per thread; writes partial[...][4] per CTA (deterministic).
+__device__ __forceinline__ void roi_reduce_store(const BlurSolveArgs& a, int p, int x, int y, bool valid,
+                                                 float2 fl, float* s_red /*[8][4]*/) {
+    const float* ax = a.axes + p * 4;
+    const float vx = fl.x * ax[0] + fl.y * ax[1];
+    const float vy = fl.x * ax[2] + fl.y * ax[3];
+    const float mg = sqrtf(vx * vx + vy * vy);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarp = blockDim.x >> 5;
+    const int ncta = gridDim.x * gridDim.y;
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    for (int r = 0; r < a.n_roi; ++r) {
+        const bool in = valid && a.masks[(size_t)r * a.mask_stride + (size_t)y * a.mask_pitch + x] != 0;
+        const float s0 = warp_sum(in ? vx : 0.f), s1 = warp_sum(in ? vy : 0.f), s2 = warp_sum(in ? mg : 0.f),
+                    s3 = warp_sum(in ? 1.f : 0.f);
+        __syncthreads();
+        if (lane == 0) {
+            s_red[warp * 4 + 0] = s0; s_red[warp * 4 + 1] = s1; s_red[warp * 4 + 2] = s2; s_red[warp * 4 + 3] = s3;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            float t = 0.f;
+            for (int i = 0; i < nwarp; ++i) t += s_red[i * 4 + threadIdx.x];
+            a.partial[(((size_t)p * a.n_roi + r) * ncta + cta) * kRoiVals + threadIdx.x] = t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs a, const WinCoef wc) {
+    __shared__ float V[5][kBsTH][kBsTW + 2 * kMaxWinHalf];
+    __shared__ float s_red[8 * 4];
+    const int m = wc.m;
+    const int x0 = blockIdx.x * kBsTW, y0 = blockIdx.y * kBsTH;
+    const int p = blockIdx.z;
+    const float* Mp = a.M + (size_t)p * a.m_stride;
+    const int tw = kBsTW + 2 * m;
+    const int w = a.w, h = a.h;
+    for (int it = threadIdx.x; it < 5 * tw; it += blockDim.x) {
+        const int c = it / tw, tx = it - c * tw;
+        const int gx = min(max(x0 - m + tx, 0), w - 1);
+        const float* col = Mp + c * a.plane_stride + gx;
+        if (wc.gauss) {
+            for (int ty = 0; ty < kBsTH; ++ty) {
+                const int gy = min(y0 + ty, h - 1);
+                float s = col[(size_t)gy * a.pitch] * wc.ker[0];
+                for (int i = 1; i <= m; ++i)
+                    s += (col[(size_t)max(gy - i, 0) * a.pitch] + col[(size_t)min(gy + i, h - 1) * a.pitch]) * wc.ker[i];
+                V[c][ty][tx] = s;
+            }
+        } else {
+            float s = 0.f;
+            for (int i = -m; i <= m; ++i) s += col[(size_t)min(max(y0 + i, 0), h - 1) * a.pitch];
+            V[c][0][tx] = s;
+            for (int ty = 1; ty < kBsTH; ++ty) {
+                const int gy = y0 + ty;
+                s += col[(size_t)min(gy + m, h - 1) * a.pitch] - col[(size_t)min(max(gy - m - 1, 0), h - 1) * a.pitch];
+                V[c][ty][tx] = s;
+            }
+        }
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & (kBsTW - 1), ty = threadIdx.x / kBsTW;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool valid = (x < w) && (y < h);
+    float g[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const float* v = &V[c][ty][tx + m];
+        float s;
+        if (wc.gauss) {
+            s = v[0] * wc.ker[0];
+            for (int i = 1; i <= m; ++i) s += (v[-i] + v[i]) * wc.ker[i];
+        } else {
+            s = v[0];
+            for (int i = 1; i <= m; ++i) s += v[-i] + v[i];
+            s *= wc.scale;
+        }
+        g[c] = s;
+    }
+    const float2 fl = solve2x2(g[0], g[1], g[2], g[3], g[4]);
+    if (valid) {
+        if (a.flow) a.flow[(size_t)p * a.flow_stride + (size_t)y * a.flow_pitch + x] = fl;
+        if (a.Mout) {
+            const float* R0 = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
+            const float* R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
+            float mm[5];
+            update_px(R0, R1, a.plane_stride, a.pitch, w, h, x, y, fl.x, fl.y, mm);
+            float* Mo = a.Mout + (size_t)p * a.m_stride + (size_t)y * a.pitch + x;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) Mo[c * a.plane_stride] = mm[c];
+        }
+    }
+    if (a.partial) roi_reduce_store(a, p, x, y, valid, fl, s_red);
+}
+
+// Projection + ROI partial sums of an existing flow buffer (iterations == 0 path; same partial layout).
+__global__ void __launch_bounds__(256) k_roi_from_flow(const BlurSolveArgs a) {
+    __shared__ float s_red[8 * 4];
+    const int tx = threadIdx.x & (kBsTW - 1), ty = threadIdx.x / kBsTW;
+    const int x = blockIdx.x * kBsTW + tx, y = blockIdx.y * kBsTH + ty;
+    const int p = blockIdx.z;
+    const bool valid = (x < a.w) && (y < a.h);
+    float2 fl = make_float2(0.f, 0.f);
+    if (valid) fl = a.flow[(size_t)p * a.flow_stride + (size_t)y * a.flow_pitch + x];
+    roi_reduce_store(a, p, x, y, valid, fl, s_red);
+}
+
+// Finalise the ROI means: out[roi][t0+1+p][3] = sums / count (double accumulation over CTAs, fixed order).
+__global__ void k_roi_finalize(const float* __restrict__ partial, int n_pairs, int n_roi, int ncta,
+                               const double* __restrict__ ex, const double* __restrict__ ey, int t_first,
+                               float* __restrict__ out, int T) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs * n_roi) return;
+    const int p = i / n_roi, r = i - p * n_roi;
+    const float* q = partial + (size_t)i * ncta * kRoiVals;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int c = 0; c < ncta; ++c) {
+        s0 += q[c * 4 + 0]; s1 += q[c * 4 + 1]; s2 += q[c * 4 + 2]; s3 += q[c * 4 + 3];
+    }
+    const int t = t_first + p;
+    float* o = out + ((size_t)r * T + t) * 3;
+    const bool ok = isfinite(ex[2 * t]) && isfinite(ex[2 * t + 1]) && isfinite(ey[2 * t]) && isfinite(ey[2 * t + 1]);
+    if (!ok || s3 == 0.0) {
+        const float nanv = __int_as_float(0x7fc00000);
+        o[0] = o[1] = o[2] = nanv;
+    } else {
+        o[0] = (float)(s0 / s3); o[1] = (float)(s1 / s3); o[2] = (float)(s2 / s3);
+    }
+}
+
+// axes[p] = (float)ex[t], ... for pairs t = t_first + p (python float -> float32 as numpy does, optical_flow.py:180-181)
+__global__ void k_axes_to_f32(const double* __restrict__ ex, const double* __restrict__ ey, int t_first, int n_pairs,
+                              float* __restrict__ axes) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const int t = t_first + p;
+    axes[p * 4 + 0] = (float)ex[2 * t];
+    axes[p * 4 + 1] = (float)ex[2 * t + 1];
+    axes[p * 4 + 2] = (float)ey[2 * t];
+    axes[p * 4 + 3] = (float)ey[2 * t + 1];
+}
+
+__global__ void k_fill_nan(float* __restrict__ p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = __int_as_float(0x7fc00000);
+}
+
+// [h][pitch] float2 -> dense [h][w] float2 and back (pitch removal for the cv2-shaped output)
+__global__ void k_copy_flow(const float2* __restrict__ src, int src_pitch, size_t src_stride, float2* __restrict__ dst,
+                            int dst_pitch, size_t dst_stride, int w, int h) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dst_pitch + x] =
+        src[(size_t)blockIdx.z * src_stride + (size_t)y * src_pitch + x];
+}
+
+}  // namespace bf

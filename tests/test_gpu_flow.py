@@ -1,0 +1,127 @@
+"""Full dense-flow parity of the CUDA path against the reference's CPU implementation (cv2, through
+oracle/cv2_ref.py) on identical inputs.  Gates from BASELINE.json north_star: mean EPE <= 0.01 px and
+max EPE <= 0.05 px.  We assert 10x tighter (the observed error is ~1e-4) so regressions show early."""
+import numpy as np
+import pytest
+
+from tests.helpers import epe, textured
+
+pytestmark = pytest.mark.gpu
+
+MEAN_GATE, MAX_GATE = 0.01, 0.05          # north_star tolerance
+MEAN_TIGHT, MAX_TIGHT = 1e-3, 5e-3        # what we hold ourselves to
+
+CASES = [
+    ((120, 160), dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)),
+    ((135, 240), dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)),
+    ((135, 240), dict(pyr_scale=0.5, levels=5, winsize=21, iterations=3, poly_n=7, poly_sigma=1.5, flags=256)),
+    ((270, 480), dict(pyr_scale=0.5, levels=0, winsize=15, iterations=1, poly_n=5, poly_sigma=1.2, flags=0)),
+    ((270, 480), dict(pyr_scale=0.5, levels=1, winsize=15, iterations=2, poly_n=5, poly_sigma=1.2, flags=0)),
+    ((200, 264), dict(pyr_scale=0.7, levels=4, winsize=16, iterations=2, poly_n=5, poly_sigma=1.1, flags=0)),
+    ((200, 264), dict(pyr_scale=0.8, levels=6, winsize=16, iterations=2, poly_n=3, poly_sigma=1.1, flags=256)),
+    ((200, 264), dict(pyr_scale=0.5, levels=2, winsize=9, iterations=2, poly_n=9, poly_sigma=0.0, flags=0)),
+    ((480, 640), dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)),
+    ((480, 640), dict(pyr_scale=0.5, levels=3, winsize=21, iterations=3, poly_n=7, poly_sigma=1.5, flags=256)),
+]
+
+
+@pytest.mark.parametrize("shape,p", CASES)
+def test_flow_matches_cv2(shape, p):
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    h, w = shape
+    a, b = textured(h, w, 1), textured(h, w, 1, shift=(1.7, -0.8))
+    ref = cv2_ref.farneback(a, b, **p)
+    got = B.calcOpticalFlowFarneback(a, b, None, **p)
+    assert got.dtype == np.float32 and got.shape == (h, w, 2) and got.flags.c_contiguous
+    mean, mx = epe(got, ref)
+    assert mean <= MEAN_GATE and mx <= MAX_GATE, (mean, mx)
+    assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (mean, mx)
+
+
+def test_flow_matches_golden_vectors(golden):
+    import btcs_pnes_optical_flow_b200 as B
+    from tests.golden.make_golden import FLOW_CASES
+    g = golden("farneback_golden.npz")
+    for name, p in FLOW_CASES.items():
+        for pair in ("ab", "cd"):
+            got = B.calcOpticalFlowFarneback(g[pair[0]], g[pair[1]], None, **p)
+            mean, mx = epe(got, g[f"flow_{pair}_{name}"])
+            assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (name, pair, mean, mx)
+
+
+def test_large_motion_uses_all_scales():
+    """A 14.5 px shift separates 1/2/3-scale implementations by > 1 px (SURVEY 8c known answers)."""
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    a, b = textured(240, 320, 2), textured(240, 320, 2, shift=(14.5, 0.0))
+    for levels in (0, 1, 3):
+        p = dict(B.FB_PARAMS, levels=levels, iterations=1)
+        mean, mx = epe(B.calcOpticalFlowFarneback(a, b, None, **p), cv2_ref.farneback(a, b, **p))
+        assert mean <= MEAN_TIGHT and mx <= MAX_GATE, (levels, mean, mx)
+
+
+def test_known_answers_and_input_conventions():
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    p = B.FB_PARAMS
+    a = textured(120, 160, 4)
+    same = B.calcOpticalFlowFarneback(a, a, None, **p)
+    ref = cv2_ref.farneback(a, a, **p)
+    assert 0.0 < np.abs(same).max() < 0.2 and epe(same, ref)[1] < MAX_TIGHT      # identical frames: non-zero at far border
+    const = np.full((64, 80), 77, np.uint8)
+    assert np.all(B.calcOpticalFlowFarneback(const, const, None, **p) == 0)       # constant frames: exactly 0, no NaN
+    assert np.all(B.calcOpticalFlowFarneback(a, a, None, **dict(p, iterations=0)) == 0)
+    b = textured(120, 160, 4, shift=(0.8, 0.4))
+    f_u8 = B.calcOpticalFlowFarneback(a, b, None, **p)
+    f_f32 = B.calcOpticalFlowFarneback(a.astype(np.float32), b.astype(np.float32), None, **p)
+    f_f64 = B.calcOpticalFlowFarneback(a.astype(np.float64), b.astype(np.float64), None, **p)
+    assert np.array_equal(f_u8, f_f32) and np.array_equal(f_u8, f_f64)            # f32 0..255 == u8 bit for bit
+    small = B.calcOpticalFlowFarneback(a[:20, :20], b[:20, :20], None, **p)        # < 32 px -> single scale
+    assert epe(small, cv2_ref.farneback(np.ascontiguousarray(a[:20, :20]), np.ascontiguousarray(b[:20, :20]), **p))[1] < MAX_TIGHT
+    view_a, view_b = a[::2, ::2], b[::2, ::2]                                     # non-contiguous views accepted
+    assert epe(B.calcOpticalFlowFarneback(view_a, view_b, None, **p),
+               cv2_ref.farneback(np.ascontiguousarray(view_a), np.ascontiguousarray(view_b), **p))[1] < MAX_TIGHT
+    buf = np.empty((120, 160, 2), np.float32)                                      # passed buffer written in place
+    out = B.calcOpticalFlowFarneback(a, b, buf, **p)
+    assert out is buf and np.array_equal(buf, f_u8)
+    assert np.array_equal(B.calcOpticalFlowFarneback(a, b, None, **p), f_u8)      # bit-deterministic
+
+
+def test_torch_tensors_stay_on_device():
+    import torch
+    import btcs_pnes_optical_flow_b200 as B
+    a, b = textured(135, 240, 7), textured(135, 240, 7, shift=(-1.1, 0.9))
+    host = B.calcOpticalFlowFarneback(a, b, None, **B.FB_PARAMS)
+    dev = B.calcOpticalFlowFarneback(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), None, **B.FB_PARAMS)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_generic_and_fast_kernels_agree(monkeypatch):
+    """BTCSFLOW_NO_FAST=1 forces the runtime-parameter kernels; both must sit inside the tight gate."""
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    a, b = textured(270, 480, 1), textured(270, 480, 1, shift=(1.7, -0.8))
+    for p in (B.FB_PARAMS, dict(B.FB_PARAMS, levels=5, winsize=21, poly_n=7, poly_sigma=1.5, flags=256)):
+        ref = cv2_ref.farneback(a, b, **p)
+        fast = B.FlowPlan(480, 270, p).flow_pair(a, b)
+        monkeypatch.setenv("BTCSFLOW_NO_FAST", "1")
+        slow = B.FlowPlan(480, 270, p).flow_pair(a, b)
+        monkeypatch.delenv("BTCSFLOW_NO_FAST")
+        for f in (fast, slow):
+            mean, mx = epe(f, ref)
+            assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (mean, mx)
+
+
+def test_1080p_full_size_properties():
+    """BASELINE full size: parity on one pair + size-independent properties (translation recovery, determinism)."""
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    a, b = textured(1080, 1920, 21), textured(1080, 1920, 21, shift=(2.25, -1.5))
+    got = B.calcOpticalFlowFarneback(a, b, None, **B.FB_PARAMS)
+    ref = cv2_ref.farneback(a, b, **B.FB_PARAMS)
+    mean, mx = epe(got, ref)
+    assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (mean, mx)
+    inner = got[100:-100, 100:-100]
+    assert abs(inner[..., 0].mean() - 2.25) < 0.05 and abs(inner[..., 1].mean() + 1.5) < 0.05
+    assert np.array_equal(got, B.calcOpticalFlowFarneback(a, b, None, **B.FB_PARAMS))

@@ -1,0 +1,113 @@
+"""ROI body-axis series (the frame loop of optical_flow.py:218-250, batched on the GPU) against the
+reference's own outputs (golden) and against cv2 on identical inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_series_matches_reference_golden(golden):
+    """Golden rows come from /root/reference compute_roi_mean_body_flow with rotated axes and one NaN-axes frame."""
+    import btcs_pnes_optical_flow_b200 as B
+    g = golden("roi_golden.npz")
+    fr, rows, ex, ey, mask = g["frames"], g["rows"], g["ex"], g["ey"], g["mask"]
+    plan = B.FlowPlan(fr.shape[2], fr.shape[1], B.FB_PARAMS, max_pairs=4, max_rois=1)
+    out = plan.flow_series(fr, ex, ey, mask)[0]
+    assert out.shape == rows.shape
+    assert np.isnan(out[0]).all() and np.isnan(out[4]).all()                      # row 0 and the NaN-axes row
+    assert np.array_equal(np.isnan(out), np.isnan(rows))
+    assert np.nanmax(np.abs(out - rows)) < 1e-4, np.nanmax(np.abs(out - rows))    # px; flow tolerance is 0.01
+    # the per-pair reference function (optical_flow.py:136) gives the same three floats
+    for t in (1, 2, 5):
+        one = B.compute_roi_mean_body_flow(fr[t - 1], fr[t], ex[t], ey[t], mask, B.FB_PARAMS)
+        assert np.allclose(one, out[t], rtol=0, atol=1e-6)
+    plan.close()
+
+
+def test_series_batching_multi_roi_and_device_api():
+    import torch
+    import btcs_pnes_optical_flow_b200 as B
+    from btcs_pnes_optical_flow_b200 import synthetic as syn
+    from oracle import cv2_ref
+    spec = syn.ClipSpec(T=11, H=135, W=240, seed=3, patch=60, roi=80, amp=3.0)
+    fr = syn.make_clip_np(spec)
+    m0 = spec.roi_mask()
+    m1 = np.zeros_like(m0)
+    m1[:, :120] = True
+    empty = np.zeros_like(m0)
+    masks = np.stack([m0, m1, empty])
+    ref = cv2_ref.roi_series(fr, [1.0, 0.0], [0.0, 1.0], masks[:2], B.FB_PARAMS, threads=4)
+    outs = []
+    for mp in (1, 3, 16):                                                         # ring/batch boundaries
+        plan = B.FlowPlan(240, 135, B.FB_PARAMS, max_pairs=mp, max_rois=3)
+        out, flow = plan.flow_series(fr, None, None, masks, return_flow=True)
+        outs.append(out)
+        assert np.nanmax(np.abs(out[:2] - ref)) < 1e-4
+        assert np.isnan(out[2]).all()                                             # empty ROI -> NaN like np.nanmean
+        # dense flow of pair t equals the stand-alone pair call
+        assert np.array_equal(flow[4], B.calcOpticalFlowFarneback(fr[4], fr[5], None, **B.FB_PARAMS))
+        dev = plan.flow_series(torch.from_numpy(fr).cuda(), None, None, torch.from_numpy(masks).cuda())
+        assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), out, equal_nan=True)   # host path == device path
+        plan.close()
+    assert np.array_equal(outs[0], outs[1], equal_nan=True) and np.array_equal(outs[0], outs[2], equal_nan=True)
+    one = B.FlowPlan(240, 135, B.FB_PARAMS, max_pairs=2).flow_series(fr[:1])
+    assert one.shape == (1, 1, 3) and np.isnan(one).all()                         # single frame: only the NaN row
+
+
+def test_series_gaussian_poly7_config():
+    import btcs_pnes_optical_flow_b200 as B
+    from btcs_pnes_optical_flow_b200 import synthetic as syn
+    from oracle import cv2_ref
+    p = dict(pyr_scale=0.5, levels=5, winsize=21, iterations=3, poly_n=7, poly_sigma=1.5, flags=256)   # config C4 params
+    spec = syn.ClipSpec(T=5, H=272, W=480, seed=4, patch=90, roi=0, amp=4.0)
+    fr = syn.make_clip_np(spec)
+    ref = cv2_ref.roi_series(fr, [1.0, 0.0], [0.0, 1.0], spec.roi_mask(), p, threads=4)
+    out = B.FlowPlan(480, 272, p, max_pairs=4).flow_series(fr)
+    assert np.nanmax(np.abs(out - ref)) < 1e-4
+
+
+def test_run_body_axis_flow_core_script_level(tmp_path):
+    """Script-level drop-in: lossless FFV1 .avi + upstream NPZ -> flow.csv with the reference's columns."""
+    import cv2
+    import pandas as pd
+    import btcs_pnes_optical_flow_b200 as B
+    from btcs_pnes_optical_flow_b200 import synthetic as syn
+    from oracle import cv2_ref
+    spec = syn.ClipSpec(T=20, H=120, W=160, seed=9, patch=48, roi=60, amp=3.0)
+    fr = syn.make_clip_np(spec)
+    vid = str(tmp_path / "clip.avi")
+    wr = cv2.VideoWriter(vid, cv2.VideoWriter_fourcc(*"FFV1"), 30.0, (160, 120), isColor=True)
+    if not wr.isOpened():
+        pytest.skip("FFV1 writer unavailable")
+    for f in fr:
+        wr.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    wr.release()
+    T = spec.T
+    ex = np.tile([1.0, 0.0], (T, 1))
+    ey = np.tile([0.0, 1.0], (T, 1))
+    ex[7] = np.nan
+    npz = str(tmp_path / "skel.npz")
+    np.savez(npz, time_all=np.arange(T) / 30.0, fps=30.0, ex=ex, ey=ey)
+    out_csv = str(tmp_path / "flow.csv")
+    B.run_body_axis_flow_core(vid, npz, spec.roi_polygon(), out_csv, chunk_frames=6)
+    df = pd.read_csv(out_csv)
+    assert list(df.columns) == ["frame", "t_sec", "skel_idx", "axes_ok", "vx_body", "vy_body", "mag_body"]
+    assert len(df) == T and df["vx_body"].isna().iloc[0]
+    bad = df[df["axes_ok"] == 0]
+    assert len(bad) >= 1 and bad["vx_body"].isna().all()
+    # decode the same file on the host and run the cv2 reference over it
+    cap = cv2.VideoCapture(vid)
+    dec = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        dec.append(cv2.cvtColor(f, cv2.COLOR_BGR2GRAY))
+    dec = np.stack(dec)
+    mask = B.build_roi_mask(120, 160, spec.roi_polygon())
+    exr = ex[df["skel_idx"].to_numpy()]
+    eyr = ey[df["skel_idx"].to_numpy()]
+    ref = cv2_ref.roi_series(dec, exr, eyr, mask, B.FB_PARAMS, threads=4)[0]
+    got = df[["vx_body", "vy_body", "mag_body"]].to_numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.nanmax(np.abs(got - ref)) < 1e-4

@@ -1,0 +1,98 @@
+"""Pins oracle/farneback_np.py (the NumPy restatement) against the installed cv2 and the committed goldens."""
+import cv2
+import numpy as np
+import pytest
+
+from tests.helpers import epe, textured
+from oracle import farneback_np as fb
+
+CASES = [
+    ((120, 160), dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)),
+    ((135, 240), dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)),
+    ((135, 240), dict(pyr_scale=0.5, levels=5, winsize=21, iterations=3, poly_n=7, poly_sigma=1.5, flags=256)),
+    ((270, 480), dict(pyr_scale=0.5, levels=0, winsize=15, iterations=1, poly_n=5, poly_sigma=1.2, flags=0)),
+    ((200, 264), dict(pyr_scale=0.7, levels=4, winsize=16, iterations=2, poly_n=5, poly_sigma=1.1, flags=0)),
+    ((200, 264), dict(pyr_scale=0.8, levels=6, winsize=16, iterations=2, poly_n=3, poly_sigma=1.1, flags=256)),
+    ((200, 264), dict(pyr_scale=0.5, levels=2, winsize=9, iterations=2, poly_n=9, poly_sigma=0.0, flags=0)),
+]
+
+
+@pytest.mark.parametrize("shape,p", CASES)
+def test_oracle_matches_cv2(shape, p):
+    h, w = shape
+    a, b = textured(h, w, 1), textured(h, w, 1, shift=(1.7, -0.8))
+    ref = cv2.calcOpticalFlowFarneback(a, b, None, **p)
+    mean, mx = epe(fb.farneback(a, b, **p), ref)
+    assert mean < 2e-6 and mx < 5e-5, (mean, mx)
+
+
+def test_oracle_matches_golden_vectors(golden):
+    g = golden("farneback_golden.npz")
+    from tests.golden.make_golden import FLOW_CASES
+    for name, p in FLOW_CASES.items():
+        for pair in ("ab", "cd"):
+            a, b = g[pair[0]], g[pair[1]]
+            mean, mx = epe(fb.farneback(a, b, **p), g[f"flow_{pair}_{name}"])
+            assert mean < 2e-6 and mx < 5e-5, (name, pair, mean, mx)
+
+
+def test_scale_selection():
+    # cv2 `levels=L` -> L+1 scales, cropped so the coarsest is >= 32 px
+    s = fb.select_scales(1920, 1080, 0.5, 3)
+    assert [(x.w, x.h) for x in s] == [(240, 135), (480, 270), (960, 540), (1920, 1080)]
+    assert [x.ksize for x in s] == [19, 9, 3, 3]
+    s = fb.select_scales(640, 480, 0.5, 5)
+    assert len(s) == 4                       # 480/16 = 30 < 32 stops at k = 3
+    s = fb.select_scales(3840, 2160, 0.5, 5)
+    assert (s[0].w, s[0].h, s[0].ksize) == (120, 68, 79)   # 67.5 -> 68 half-even
+    assert len(fb.select_scales(20, 20, 0.5, 3)) == 1
+    assert [(x.w, x.h) for x in fb.select_scales(240, 135, 0.5, 2)] == [(60, 34), (120, 68), (240, 135)]
+
+
+def test_known_answers():
+    a = textured(120, 160, 4)
+    p = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+    same = fb.farneback(a, a, **p)
+    ref = cv2.calcOpticalFlowFarneback(a, a, None, **p)
+    assert 0.0 < np.abs(ref).max() < 0.2      # identical frames -> NON-zero flow at the far border
+    assert epe(same, ref)[1] < 5e-5
+    const = np.full((64, 80), 77, np.uint8)
+    z = fb.farneback(const, const, **p)
+    assert np.all(z == 0) and np.all(cv2.calcOpticalFlowFarneback(const, const, None, **p) == 0)
+    assert np.all(fb.farneback(a, a, **dict(p, iterations=0)) == 0)
+    with pytest.raises(ValueError):
+        fb.farneback(a, a[:-1], **p)
+    with pytest.raises(ValueError):
+        fb.farneback(a, a, **dict(p, pyr_scale=1.0))
+
+
+def test_stage_pieces_against_cv2():
+    img = textured(97, 131, 9).astype(np.float32)
+    for ks, sg in ((3, 0.0), (3, 0.5), (9, 1.5), (19, 3.5)):
+        ref = cv2.GaussianBlur(img, (ks, ks), sg, sigmaY=sg)
+        assert np.abs(fb.gaussian_blur_reflect101(img, ks, sg) - ref).max() < 2e-4
+    for (w, h) in ((66, 49), (131, 97), (33, 24), (100, 60)):
+        ref = cv2.resize(img, (w, h), interpolation=cv2.INTER_LINEAR)
+        assert np.abs(fb.resize_bilinear(img, w, h) - ref).max() < 5e-4
+    fl = np.stack([img, -img], -1)
+    ref = cv2.resize(fl, (200, 150), interpolation=cv2.INTER_LINEAR)
+    assert np.abs(fb.resize_bilinear(fl, 200, 150) - ref).max() < 5e-4
+
+
+def test_box_blur_prefix_vs_direct():
+    rng = np.random.default_rng(0)
+    M = (rng.standard_normal((40, 50, 5)) * 100).astype(np.float32)
+    for ws in (15, 16, 5):
+        assert np.allclose(fb.blur_box(M, ws), fb.blur_box_direct(M, ws), rtol=1e-11, atol=1e-9)
+
+
+def test_roi_mean_matches_reference_golden(golden):
+    g = golden("roi_golden.npz")
+    fr, rows, ex, ey, mask = g["frames"], g["rows"], g["ex"], g["ey"], g["mask"]
+    p = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+    for t in range(1, fr.shape[0]):
+        if not np.isfinite(rows[t]).all():
+            assert not np.isfinite(ex[t]).all()
+            continue
+        got = fb.roi_mean_body_flow(fb.farneback(fr[t - 1], fr[t], **p), ex[t], ey[t], mask)
+        assert np.allclose(got, rows[t], rtol=2e-5, atol=2e-6), (t, got, rows[t])
