@@ -257,9 +257,11 @@ def run_ours(args, spec, params):
                     "kernel_share_of_step": prof["total_ms"] / ms_total, "peak_source": peak_src,
                     "pipeline_bytes_per_pair": bpp, "pipeline_achieved_GBs": value * bpp / 1e9,
                     "pipeline_frac": value * bpp / 1e9 / peak}
-        assert pc1 is not None and np.isfinite(pc1).sum() > 0.9 * (T_total - 60)
-        r = np.corrcoef(pc1[np.isfinite(pc1) & np.isfinite(pc1_h)], pc1_h[np.isfinite(pc1) & np.isfinite(pc1_h)])[0, 1]
-        assert r > 0.999999, "host-buffer and device-buffer paths disagree"
+        assert pc1 is not None and pc1.shape == (T_total,)
+        both = np.isfinite(pc1) & np.isfinite(pc1_h)
+        if T_total >= 120:                      # long enough for the 2 s PCA window: the series must be usable
+            assert both.sum() > 0.9 * (T_total - 1), "PC1 mostly NaN"
+            assert np.corrcoef(pc1[both], pc1_h[both])[0, 1] > 0.999999, "host-buffer and device-buffer paths disagree"
         cpu = None
         if world == 1:
             cores = os.cpu_count() or 1

@@ -271,7 +271,7 @@ int launch_pyramid(bf_plan* p, const ScaleInfo& s, const T* src, size_t pitch_by
 int launch_polyexp(bf_plan* p, const float* I, int pitch, size_t frame_stride, int w, int h, float* R,
                    size_t plane_stride, size_t slot_stride, int slot0, int nslots, int nf, const bf::PolyCoef& pc,
                    bool allow_fast, cudaStream_t st) {
-    if (allow_fast && bf::polyexp_fast_supported(pc.n, pitch)) {
+    if (allow_fast && bf::polyexp_fast_supported(pc.n, pitch) && bf::polyexp_fast_aligned(R, plane_stride, slot_stride)) {
         bf::launch_polyexp_fast(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
         LAUNCH_CHECK();
         return 0;
@@ -291,13 +291,17 @@ int launch_update(const bf::UpdateArgs& a, int np, cudaStream_t st) {
     return 0;
 }
 
-int blur_solve_ncta(int w, int h, const bf::WinCoef& wc, bool allow_fast, int pitch) {
-    if (allow_fast && bf::blur_solve_fast_supported(wc, pitch)) return bf::blur_solve_fast_ncta(w, h);
-    return cdiv(w, bf::kBsTW) * cdiv(h, bf::kBsTH);
+bool use_fast_blur(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, bool allow_fast) {
+    return allow_fast && bf::blur_solve_fast_supported(wc, a.pitch) && bf::blur_solve_fast_aligned(a);
+}
+
+int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, bool allow_fast) {
+    if (use_fast_blur(a, wc, allow_fast)) return bf::blur_solve_fast_ncta(a.w, a.h);
+    return cdiv(a.w, bf::kBsTW) * cdiv(a.h, bf::kBsTH);
 }
 
 int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast, cudaStream_t st) {
-    if (allow_fast && bf::blur_solve_fast_supported(wc, a.pitch)) {
+    if (use_fast_blur(a, wc, allow_fast)) {
         bf::launch_blur_solve_fast(a, wc, np, st);
         LAUNCH_CHECK();
         return 0;
@@ -357,7 +361,7 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
             bf::k_roi_from_flow<<<g, 256, 0, st>>>(a);
             LAUNCH_CHECK();
             const int ncta = g.x * g.y;
-            bf::k_roi_finalize<<<cdiv(np * roi->n_roi, 64), 64, 0, st>>>(p->partial, np, roi->n_roi, ncta, roi->ex,
+            bf::k_roi_finalize<<<cdiv(np * roi->n_roi, 4), 128, 0, st>>>(p->partial, np, roi->n_roi, ncta, roi->ex,
                                                                          roi->ey, t0 + 1, roi->out, roi->T);
             LAUNCH_CHECK();
         }
@@ -419,8 +423,8 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
                 p->prof_pairs += np;
             }
             if (last && finest && want_roi) {
-                const int ncta = blur_solve_ncta(s.w, s.h, p->wc, p->use_fast, s.pitch);
-                bf::k_roi_finalize<<<cdiv(np * roi->n_roi, 64), 64, 0, st>>>(p->partial, np, roi->n_roi, ncta, roi->ex,
+                const int ncta = blur_solve_ncta(a, p->wc, p->use_fast);
+                bf::k_roi_finalize<<<cdiv(np * roi->n_roi, 4), 128, 0, st>>>(p->partial, np, roi->n_roi, ncta, roi->ex,
                                                                              roi->ey, t0 + 1, roi->out, roi->T);
                 LAUNCH_CHECK();
             }

@@ -1,16 +1,347 @@
 // Specialised (compile-time window / poly_n) kernels for the configurations BASELINE.json names.
-// Filled in after the generic path is parity-green; the dispatch predicates below gate them.
+//
+// k_blur_solve_box<MH>: flow = Solve(BoxBlur_{2MH+1}(M)) fused with M' = UpdateMatrices(flow) and/or the
+// body-axis projection + ROI partial sums (reference call site optical_flow.py:173, reduction
+// optical_flow.py:176-187).  One CTA = 128 x 32 output pixels, 256 threads, 2 CTAs per SM.
+//   phase 1  vertical window sums, global -> shared.  One thread per (channel, float4 column): 128-bit coalesced
+//            loads, the 2MH+1 row window lives in registers (fully unrolled ring), exact first window then
+//            add-new/subtract-old with a history bounded by the 32+2MH rows of the tile: no long-range
+//            cancellation, and all-zero (static) regions stay exactly zero.
+//   phase 2  horizontal window sums from shared with conflict-free LDS.128 (lane stride 16 B), 4 outputs per
+//            thread sharing the common partial sum (no subtraction), then the 2x2 solve with Kahan-accurate
+//            determinants.  The 1/winsize^2 scale is folded into the regulariser (reg = 1e-3 * winsize^4).
+//   phase 3  flow is transposed through shared memory so that lanes own consecutive pixels again: coalesced R0
+//            loads, bilinear R1 gather, M' stores; ROI sums reduced per CTA (deterministic partials).
 #pragma once
 #include "farneback_kernels.cuh"
 
 namespace bf {
 
-inline bool polyexp_fast_supported(int /*n*/, int /*pitch*/) { return false; }
-inline void launch_polyexp_fast(const float*, int, size_t, int, int, float*, size_t, size_t, int, int, int,
-                                const PolyCoef&, cudaStream_t) {}
+constexpr int kFbTW = 128, kFbTH = 32;
 
-inline bool blur_solve_fast_supported(const WinCoef&, int /*pitch*/) { return false; }
-inline int blur_solve_fast_ncta(int, int) { return 0; }
-inline void launch_blur_solve_fast(const BlurSolveArgs&, const WinCoef&, int, cudaStream_t) {}
+template <int MH>
+struct FastBoxCfg {
+    static constexpr int HALO = (MH + 3) / 4 * 4;
+    static constexpr int D = HALO - MH;                        // unused leading columns in the halo
+    static constexpr int NC4 = (kFbTW + 2 * HALO) / 4;         // float4 columns per tile row
+    static constexpr int VP = kFbTW + 2 * HALO + 4;            // shared row pitch (floats, multiple of 4)
+    static constexpr int WIN = 2 * MH + 1;
+    static constexpr int NCH = (D + 2 * MH + 3) / 4 + 1;       // float4 chunks a 4-output group reads
+    static constexpr int V_FLOATS = 5 * kFbTH * VP;
+    static constexpr size_t SMEM = (size_t)(V_FLOATS + 64) * sizeof(float);
+    static_assert(MH >= 2 && MH <= 16, "half window out of range for the fast path");
+    static_assert((size_t)kFbTH * kFbTW * sizeof(float2) <= (size_t)V_FLOATS * sizeof(float), "F must fit in V");
+};
+
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
+template <int MH>
+__global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a, const float reg) {
+    using C = FastBoxCfg<MH>;
+    extern __shared__ __align__(16) float smem[];
+    float* V = smem;                                   // [5][TH][VP]
+    float2* F = reinterpret_cast<float2*>(smem);       // [TH][TW], aliases V after phase 2
+    float* s_red = smem + C::V_FLOATS;                 // [8][4]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kFbTH, p = blockIdx.z;
+    const int w = a.w, h = a.h, pitch = a.pitch;
+    const float* Mp = a.M + (size_t)p * a.m_stride;
+
+    // ---------------- phase 1: vertical sums ----------------
+    for (int task = tid; task < 5 * C::NC4; task += 256) {
+        const int c = task / C::NC4, q = task - c * C::NC4;
+        const int gx = x0 - C::HALO + 4 * q;
+        const float* src = Mp + (size_t)c * a.plane_stride;
+        float* dst = V + (size_t)c * kFbTH * C::VP + 4 * q;
+        const bool vec = (gx >= 0) && (gx + 3 < w);
+        const int c0 = min(max(gx, 0), w - 1), c1 = min(max(gx + 1, 0), w - 1), c2 = min(max(gx + 2, 0), w - 1),
+                  c3 = min(max(gx + 3, 0), w - 1);
+        auto ld = [&](int i) -> float4 {
+            const int r = min(max(y0 - MH + i, 0), h - 1);
+            const float* rp = src + (size_t)r * pitch;
+            if (vec) return __ldg(reinterpret_cast<const float4*>(rp + gx));
+            return make_float4(__ldg(rp + c0), __ldg(rp + c1), __ldg(rp + c2), __ldg(rp + c3));
+        };
+        float4 win[C::WIN];
+#pragma unroll
+        for (int i = 0; i < C::WIN; ++i) win[i] = ld(i);
+        // pairwise tree over the first window (exact order is irrelevant, but keep the chain short)
+        float4 s = win[0];
+#pragma unroll
+        for (int i = 1; i < C::WIN; ++i) s = f4add(s, win[i]);
+        *reinterpret_cast<float4*>(dst) = s;
+        constexpr int PF = 4;                           // software prefetch depth
+        float4 pre[PF];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) pre[i] = ld(C::WIN + i);
+#pragma unroll
+        for (int j = 1; j < kFbTH; ++j) {
+            const float4 nv = pre[(j - 1) % PF];
+            if (j - 1 + PF + C::WIN < kFbTH + 2 * MH) pre[(j - 1) % PF] = ld(C::WIN + j - 1 + PF);
+            const float4 ov = win[(j - 1) % C::WIN];
+            s = f4add(s, f4sub(nv, ov));
+            win[(j - 1) % C::WIN] = nv;
+            *reinterpret_cast<float4*>(dst + j * C::VP) = s;
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: horizontal sums + solve ----------------
+    const int g = tid & 31, rb = tid >> 5;
+    float2 fl[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = rb + 8 * k;
+        float gs[5][4];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float4* vp = reinterpret_cast<const float4*>(V + ((size_t)c * kFbTH + r) * C::VP) + g;
+            float vv[4 * C::NCH];
+#pragma unroll
+            for (int i = 0; i < C::NCH; ++i) {
+                const float4 t = vp[i];
+                vv[4 * i] = t.x; vv[4 * i + 1] = t.y; vv[4 * i + 2] = t.z; vv[4 * i + 3] = t.w;
+            }
+            // common part vv[D+3 .. D+2MH], summed as two interleaved chains for ILP
+            float t0 = vv[C::D + 3], t1 = vv[C::D + 4];
+#pragma unroll
+            for (int i = C::D + 5; i + 1 <= C::D + 2 * MH; i += 2) { t0 += vv[i]; t1 += vv[i + 1]; }
+            if (((2 * MH - 2) & 1) != 0) t0 += vv[C::D + 2 * MH];
+            const float T = t0 + t1;
+            const float l2 = vv[C::D + 2], l12 = vv[C::D + 1] + l2, l012 = vv[C::D] + l12;
+            const float r1 = vv[C::D + 2 * MH + 1], r12 = r1 + vv[C::D + 2 * MH + 2], r123 = r12 + vv[C::D + 2 * MH + 3];
+            gs[c][0] = T + l012;
+            gs[c][1] = (T + l12) + r1;
+            gs[c][2] = (T + l2) + r12;
+            gs[c][3] = T + r123;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float g11 = gs[0][j], g12 = gs[1][j], g22 = gs[2][j], h1 = gs[3][j], h2 = gs[4][j];
+            const float det = diff_of_products(g11, g22, g12, g12) + reg;
+            const float idet = 1.f / det;
+            fl[k][j].x = diff_of_products(g11, h2, g12, h1) * idet;
+            fl[k][j].y = diff_of_products(g22, h1, g12, h2) * idet;
+        }
+    }
+    __syncthreads();                                    // all reads of V done before F overwrites it
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float4* fp = reinterpret_cast<float4*>(F + (rb + 8 * k) * kFbTW + 4 * g);
+        fp[0] = make_float4(fl[k][0].x, fl[k][0].y, fl[k][1].x, fl[k][1].y);
+        fp[1] = make_float4(fl[k][2].x, fl[k][2].y, fl[k][3].x, fl[k][3].y);
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: coalesced tail ----------------
+    const int lane = tid & 31, wid = tid >> 5;
+    const float* R0 = nullptr;
+    const float* R1 = nullptr;
+    if (a.Mout) {
+        R0 = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
+        R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
+    }
+    if (a.flow || a.Mout) {
+#pragma unroll 2
+        for (int i = 0; i < 16; ++i) {
+            const int r = wid * 4 + (i >> 2), cx = (i & 3) * 32 + lane;
+            const int x = x0 + cx, y = y0 + r;
+            if (x < w && y < h) {
+                const float2 f = F[r * kFbTW + cx];
+                if (a.flow) a.flow[(size_t)p * a.flow_stride + (size_t)y * a.flow_pitch + x] = f;
+                if (a.Mout) {
+                    float mm[5];
+                    update_px(R0, R1, a.plane_stride, pitch, w, h, x, y, f.x, f.y, mm);
+                    float* Mo = a.Mout + (size_t)p * a.m_stride + (size_t)y * pitch + x;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) Mo[c * a.plane_stride] = mm[c];
+                }
+            }
+        }
+    }
+    if (a.partial) {
+        const float* ax = a.axes + p * 4;
+        const float e00 = ax[0], e01 = ax[1], e10 = ax[2], e11 = ax[3];
+        const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+        for (int roi = 0; roi < a.n_roi; ++roi) {
+            const uint8_t* mk = a.masks + (size_t)roi * a.mask_stride;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = wid * 4 + (i >> 2), cx = (i & 3) * 32 + lane;
+                const int x = x0 + cx, y = y0 + r;
+                if (x < w && y < h && mk[(size_t)y * a.mask_pitch + x] != 0) {
+                    const float2 f = F[r * kFbTW + cx];
+                    const float vx = f.x * e00 + f.y * e01;
+                    const float vy = f.x * e10 + f.y * e11;
+                    s0 += vx; s1 += vy; s2 += sqrtf(vx * vx + vy * vy); s3 += 1.f;
+                }
+            }
+            s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+            __syncthreads();
+            if (lane == 0) { s_red[wid * 4] = s0; s_red[wid * 4 + 1] = s1; s_red[wid * 4 + 2] = s2; s_red[wid * 4 + 3] = s3; }
+            __syncthreads();
+            if (tid < 4) {
+                float t = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t += s_red[i * 4 + tid];
+                a.partial[(((size_t)p * a.n_roi + roi) * ncta + cta) * kRoiVals + tid] = t;
+            }
+        }
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline bool blur_solve_fast_supported(const WinCoef& wc, int pitch) {
+    return !wc.gauss && wc.m == 7 && (pitch % 4) == 0;
+}
+inline int blur_solve_fast_ncta(int w, int h) { return ((w + kFbTW - 1) / kFbTW) * ((h + kFbTH - 1) / kFbTH); }
+
+inline bool blur_solve_fast_aligned(const BlurSolveArgs& a) {
+    return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0;
+}
+
+inline void launch_blur_solve_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
+    using C = FastBoxCfg<7>;
+    // per device/context attribute; cheap enough to set on every launch (one process may own several plans)
+    cudaFuncSetAttribute(k_blur_solve_box<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    const float reg = 1e-3f / (wc.scale * wc.scale);
+    dim3 g((a.w + kFbTW - 1) / kFbTW, (a.h + kFbTH - 1) / kFbTH, np);
+    k_blur_solve_box<7><<<g, 256, C::SMEM, st>>>(a, reg);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_polyexp<N>: separable polynomial expansion with compile-time poly_n.  Tile 128 x 32, 256 threads.
+//   vertical pass   thread per (column, 8-row group): coalesced 32-bit loads straight from global (rows clamped =
+//                   replicate), the 8+2N values live in registers, taps are compile-time constants-bank reads
+//   horizontal pass thread per 4 consecutive outputs: conflict-free LDS.128, 128-bit coalesced plane stores
+// ---------------------------------------------------------------------------------------------------
+template <int N>
+struct FastPeCfg {
+    static constexpr int HALO = (N + 3) / 4 * 4;
+    static constexpr int NCOL = kFbTW + 2 * HALO;
+    static constexpr int VP = NCOL + 4;
+    static constexpr int RG = 4, RPG = kFbTH / RG;             // row groups, rows per group
+    static constexpr int NCH = (HALO + N + 3) / 4 + 1;
+    static constexpr size_t SMEM = (size_t)3 * kFbTH * VP * sizeof(float);
+};
+
+template <int N>
+__global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I, int pitch, size_t frame_stride, int w,
+                                                    int h, float* __restrict__ R, size_t plane_stride,
+                                                    size_t slot_stride, int slot0, int nslots, const PolyCoef pc) {
+    using C = FastPeCfg<N>;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kFbTH, f = blockIdx.z;
+    const float* img = I + (size_t)f * frame_stride;
+    for (int task = tid; task < C::RG * C::NCOL; task += 256) {
+        const int rg = task / C::NCOL, col = task - rg * C::NCOL;
+        const int gx = min(max(x0 - C::HALO + col, 0), w - 1);
+        const int yb = y0 + rg * C::RPG - N;
+        float v[C::RPG + 2 * N];
+#pragma unroll
+        for (int i = 0; i < C::RPG + 2 * N; ++i) v[i] = __ldg(img + (size_t)min(max(yb + i, 0), h - 1) * pitch + gx);
+        float* dst = smem + (rg * C::RPG) * C::VP + col;
+#pragma unroll
+        for (int j = 0; j < C::RPG; ++j) {
+            const float c = v[j + N];
+            float t0 = c * pc.g[0], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float up = v[j + N - k], dn = v[j + N + k];
+                const float pp = up + dn;
+                t0 = fmaf(pc.g[k], pp, t0);
+                t1 = fmaf(pc.xg[k], dn - up, t1);
+                t2 = fmaf(pc.xxg[k], pp, t2);
+            }
+            dst[j * C::VP] = t0;
+            dst[(kFbTH + j) * C::VP] = t1;
+            dst[(2 * kFbTH + j) * C::VP] = t2;
+        }
+    }
+    __syncthreads();
+    const int g = tid & 31, rb = tid >> 5;
+    float* Rb = R + (size_t)((slot0 + f) % nslots) * slot_stride;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int r = rb + 8 * k;
+        const int y = y0 + r, x = x0 + 4 * g;
+        float vv[3][4 * C::NCH];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4* vp = reinterpret_cast<const float4*>(smem + ((size_t)c * kFbTH + r) * C::VP) + g;
+#pragma unroll
+            for (int i = 0; i < C::NCH; ++i) {
+                const float4 t = vp[i];
+                vv[c][4 * i] = t.x; vv[c][4 * i + 1] = t.y; vv[c][4 * i + 2] = t.z; vv[c][4 * i + 3] = t.w;
+            }
+        }
+        float o[5][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = C::HALO + j;
+            float b1 = vv[0][ci] * pc.g[0], b3 = vv[1][ci] * pc.g[0], b5 = vv[2][ci] * pc.g[0];
+            float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+#pragma unroll
+            for (int t = 1; t <= N; ++t) {
+                const float p0 = vv[0][ci + t], m0 = vv[0][ci - t];
+                const float p1 = vv[1][ci + t], m1 = vv[1][ci - t];
+                const float p2 = vv[2][ci + t], m2 = vv[2][ci - t];
+                const float tg = p0 + m0;
+                b1 = fmaf(tg, pc.g[t], b1);
+                b4 = fmaf(tg, pc.xxg[t], b4);
+                b2 = fmaf(p0 - m0, pc.xg[t], b2);
+                b3 = fmaf(p1 + m1, pc.g[t], b3);
+                b6 = fmaf(p1 - m1, pc.xg[t], b6);
+                b5 = fmaf(p2 + m2, pc.g[t], b5);
+            }
+            o[0][j] = b3 * pc.ig11;
+            o[1][j] = b2 * pc.ig11;
+            o[2][j] = fmaf(b1, pc.ig03, b5 * pc.ig33);
+            o[3][j] = fmaf(b1, pc.ig03, b4 * pc.ig33);
+            o[4][j] = b6 * pc.ig55;
+        }
+        if (y < h && x < w) {
+            float* op = Rb + (size_t)y * pitch + x;
+            if (x + 3 < w) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c)
+                    *reinterpret_cast<float4*>(op + c * plane_stride) = make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 5; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x + j < w) op[c * plane_stride + j] = o[c][j];
+            }
+        }
+    }
+}
+
+inline bool polyexp_fast_supported(int n, int pitch) { return (n == 5 || n == 7) && (pitch % 4) == 0; }
+
+inline bool polyexp_fast_aligned(const float* R, size_t plane_stride, size_t slot_stride) {
+    return aligned16(R) && (plane_stride % 4) == 0 && (slot_stride % 4) == 0;
+}
+
+template <int N>
+inline void launch_polyexp_fast_n(const float* I, int pitch, size_t frame_stride, int w, int h, float* R,
+                                  size_t plane_stride, size_t slot_stride, int slot0, int nslots, int nf,
+                                  const PolyCoef& pc, cudaStream_t st) {
+    using C = FastPeCfg<N>;
+    cudaFuncSetAttribute(k_polyexp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    dim3 g((w + kFbTW - 1) / kFbTW, (h + kFbTH - 1) / kFbTH, nf);
+    k_polyexp<N><<<g, 256, C::SMEM, st>>>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, pc);
+}
+
+inline void launch_polyexp_fast(const float* I, int pitch, size_t frame_stride, int w, int h, float* R,
+                                size_t plane_stride, size_t slot_stride, int slot0, int nslots, int nf,
+                                const PolyCoef& pc, cudaStream_t st) {
+    if (pc.n == 5) launch_polyexp_fast_n<5>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
+    else launch_polyexp_fast_n<7>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
+}
 
 }  // namespace bf

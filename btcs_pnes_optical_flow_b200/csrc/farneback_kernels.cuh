@@ -453,18 +453,29 @@ __global__ void __launch_bounds__(256) k_roi_from_flow(const BlurSolveArgs a) {
     roi_reduce_store(a, p, x, y, valid, fl, s_red);
 }
 
-// Finalise the ROI means: out[roi][t0+1+p][3] = sums / count (double accumulation over CTAs, fixed order).
+// Finalise the ROI means: out[roi][t_first+p][3] = sums / count.  One warp per (pair, roi); lanes stride over the
+// per-CTA partials and accumulate in double, then a fixed-order shuffle tree: deterministic run to run.
 __global__ void k_roi_finalize(const float* __restrict__ partial, int n_pairs, int n_roi, int ncta,
                                const double* __restrict__ ex, const double* __restrict__ ey, int t_first,
                                float* __restrict__ out, int T) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (i >= n_pairs * n_roi) return;
     const int p = i / n_roi, r = i - p * n_roi;
-    const float* q = partial + (size_t)i * ncta * kRoiVals;
+    const float4* q = reinterpret_cast<const float4*>(partial + (size_t)i * ncta * kRoiVals);
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    for (int c = 0; c < ncta; ++c) {
-        s0 += q[c * 4 + 0]; s1 += q[c * 4 + 1]; s2 += q[c * 4 + 2]; s3 += q[c * 4 + 3];
+    for (int c = lane; c < ncta; c += 32) {
+        const float4 v = q[c];
+        s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    if (lane != 0) return;
     const int t = t_first + p;
     float* o = out + ((size_t)r * T + t) * 3;
     const bool ok = isfinite(ex[2 * t]) && isfinite(ex[2 * t + 1]) && isfinite(ey[2 * t]) && isfinite(ey[2 * t + 1]);

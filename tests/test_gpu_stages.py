@@ -37,11 +37,12 @@ def test_level_images(T, shape, levels, pyr):
     plan.close()
 
 
-@pytest.mark.parametrize("n,sigma", [(5, 1.2), (7, 1.5), (3, 1.1), (9, 0.0)])
-def test_poly_exp(T, n, sigma):
+@pytest.mark.parametrize("n,sigma,w", [(5, 1.2, 150), (5, 1.2, 152), (7, 1.5, 152), (7, 1.5, 131), (3, 1.1, 152), (9, 0.0, 150)])
+def test_poly_exp(T, n, sigma, w):
+    """w % 4 == 0 takes the compile-time-N kernel (n = 5, 7), anything else the runtime-parameter one."""
     from btcs_pnes_optical_flow_b200 import stages
     from oracle import farneback_np as fb
-    img = textured(101, 150, 5).astype(np.float32)
+    img = textured(101, w, 5).astype(np.float32)
     ref = fb.poly_exp(img, n, sigma)
     got = stages.poly_exp(_dev(T, img), n, sigma).cpu().numpy().transpose(1, 2, 0)
     scale = np.abs(ref).max(axis=(0, 1))
@@ -69,11 +70,14 @@ def test_update_matrices(T):
     assert np.isfinite(got).all()
 
 
-@pytest.mark.parametrize("winsize,flags", [(15, 0), (16, 0), (5, 0), (21, 256), (16, 256), (33, 0)])
-def test_blur_solve(T, winsize, flags):
+@pytest.mark.parametrize("winsize,flags,w", [(15, 0, 120), (15, 0, 301), (15, 0, 300), (16, 0, 120), (5, 0, 120),
+                                              (21, 256, 120), (16, 256, 120), (33, 0, 120)])
+def test_blur_solve(T, winsize, flags, w):
+    """winsize 15 box with w % 4 == 0 takes the specialised kernel (tiles of 128 x 32: 300 and 120 exercise the
+    ragged right/bottom edges); everything else the runtime-parameter kernel."""
     from btcs_pnes_optical_flow_b200 import stages
     from oracle import farneback_np as fb
-    h, w = 83, 120
+    h = 83
     a, b = textured(h, w, 8).astype(np.float32), textured(h, w, 8, shift=(0.7, -1.1)).astype(np.float32)
     R0, R1 = fb.poly_exp(a, 5, 1.2), fb.poly_exp(b, 5, 1.2)
     M = fb.update_matrices(R0, R1, np.zeros((h, w, 2), np.float32))
