@@ -33,8 +33,48 @@ struct FastBoxCfg {
     static_assert((size_t)kFbTH * kFbTW * sizeof(float2) <= (size_t)V_FLOATS * sizeof(float), "F must fit in V");
 };
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
+// Vertical (2MH+1)-row box sums of one float4 column for kFbTH consecutive output rows; register ring window, software
+// prefetch 4 rows ahead.  ROWS_IN: the tile's rows (with halo) lie inside the image, `src` already points at the first
+// halo row.  Otherwise rows are clamped to [0, h-1] (replicate) starting from row `yb`.
+template <int MH, bool ROWS_IN>
+__device__ __forceinline__ void vertical_box_sums(const float* __restrict__ src, unsigned pitch, int yb, int h, int mode,
+                                                  float* __restrict__ dst, int vp) {
+    constexpr int WIN = 2 * MH + 1, PF = 4, NROW = kFbTH + 2 * MH;
+    auto ld = [&](int i) -> float4 {
+        if (ROWS_IN) return __ldg(reinterpret_cast<const float4*>(src + (unsigned)i * pitch));
+        const int r = min(max(yb + i, 0), h - 1);
+        return __ldg(reinterpret_cast<const float4*>(src + (unsigned)r * pitch));
+    };
+    auto st = [&](int j, const float4& s) {
+        float4 o = s;
+        if (mode == 1) o = make_float4(s.x, s.x, s.x, s.x);
+        else if (mode == 2) o = make_float4(s.w, s.w, s.w, s.w);
+        *reinterpret_cast<float4*>(dst + j * vp) = o;
+    };
+    float4 win[WIN];
+#pragma unroll
+    for (int i = 0; i < WIN; ++i) win[i] = ld(i);
+    float4 s = win[0];
+#pragma unroll
+    for (int i = 1; i < WIN; ++i) s = f4add(s, win[i]);
+    st(0, s);
+    float4 pre[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) pre[i] = ld(WIN + i);
+#pragma unroll
+    for (int j = 1; j < kFbTH; ++j) {
+        const float4 nv = pre[(j - 1) % PF];
+        if (j - 1 + PF + WIN < NROW) pre[(j - 1) % PF] = ld(WIN + j - 1 + PF);
+        const float4 ov = win[(j - 1) % WIN];
+        s = f4add(s, f4sub(nv, ov));
+        win[(j - 1) % WIN] = nv;
+        st(j, s);
+    }
+}
 
 template <int MH>
 __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a, const float reg) {
@@ -45,45 +85,42 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a
     float* s_red = smem + C::V_FLOATS;                 // [8][4]
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kFbTH, p = blockIdx.z;
-    const int w = a.w, h = a.h, pitch = a.pitch;
+    const int w = a.w, h = a.h;
+    const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
     const float* Mp = a.M + (size_t)p * a.m_stride;
 
+    // L2 prefetch of what phase 3 will read (R0 under the tile, R1 around it): the lines travel from HBM while
+    // phases 1-2 run, so the gather later pays L2 latency instead of DRAM latency.
+    if (a.Mout) {
+        const float* R0p = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
+        const float* R1p = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
+        const int xmax = (int)pitch - 32;
+        for (int e = tid; e < 5 * kFbTH * 4; e += 256) {
+            const int c = e / (kFbTH * 4), rem = e - c * (kFbTH * 4);
+            const int yy = min(y0 + (rem >> 2), h - 1), xx = min(x0 + (rem & 3) * 32, xmax);
+            prefetch_l2(R0p + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
+        }
+        for (int e = tid; e < 5 * (kFbTH + 4) * 6; e += 256) {
+            const int c = e / ((kFbTH + 4) * 6), rem = e - c * ((kFbTH + 4) * 6);
+            const int yy = min(max(y0 - 2 + rem / 6, 0), h - 1), xx = min(max(x0 - 32 + (rem % 6) * 32, 0), xmax);
+            prefetch_l2(R1p + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
+        }
+    }
+
     // ---------------- phase 1: vertical sums ----------------
+    // w % 4 == 0 and float4-aligned columns: a float4 column is entirely inside the image, entirely left of it or
+    // entirely right of it.  Outside columns load the nearest inside chunk and splat its edge lane when the SUM is
+    // stored (replicate border; splat commutes with the sum), so the load path is branch-free.
+    const bool rows_in = (y0 - MH >= 0) && (y0 + kFbTH + MH <= h);      // block-uniform: no row clamping needed
     for (int task = tid; task < 5 * C::NC4; task += 256) {
         const int c = task / C::NC4, q = task - c * C::NC4;
         const int gx = x0 - C::HALO + 4 * q;
-        const float* src = Mp + (size_t)c * a.plane_stride;
+        const int mode = gx < 0 ? 1 : (gx >= w ? 2 : 0);
+        const int cgx = mode == 1 ? 0 : (mode == 2 ? w - 4 : gx);
+        const float* src = Mp + (size_t)c * plane + (unsigned)cgx;
         float* dst = V + (size_t)c * kFbTH * C::VP + 4 * q;
-        const bool vec = (gx >= 0) && (gx + 3 < w);
-        const int c0 = min(max(gx, 0), w - 1), c1 = min(max(gx + 1, 0), w - 1), c2 = min(max(gx + 2, 0), w - 1),
-                  c3 = min(max(gx + 3, 0), w - 1);
-        auto ld = [&](int i) -> float4 {
-            const int r = min(max(y0 - MH + i, 0), h - 1);
-            const float* rp = src + (size_t)r * pitch;
-            if (vec) return __ldg(reinterpret_cast<const float4*>(rp + gx));
-            return make_float4(__ldg(rp + c0), __ldg(rp + c1), __ldg(rp + c2), __ldg(rp + c3));
-        };
-        float4 win[C::WIN];
-#pragma unroll
-        for (int i = 0; i < C::WIN; ++i) win[i] = ld(i);
-        // pairwise tree over the first window (exact order is irrelevant, but keep the chain short)
-        float4 s = win[0];
-#pragma unroll
-        for (int i = 1; i < C::WIN; ++i) s = f4add(s, win[i]);
-        *reinterpret_cast<float4*>(dst) = s;
-        constexpr int PF = 4;                           // software prefetch depth
-        float4 pre[PF];
-#pragma unroll
-        for (int i = 0; i < PF; ++i) pre[i] = ld(C::WIN + i);
-#pragma unroll
-        for (int j = 1; j < kFbTH; ++j) {
-            const float4 nv = pre[(j - 1) % PF];
-            if (j - 1 + PF + C::WIN < kFbTH + 2 * MH) pre[(j - 1) % PF] = ld(C::WIN + j - 1 + PF);
-            const float4 ov = win[(j - 1) % C::WIN];
-            s = f4add(s, f4sub(nv, ov));
-            win[(j - 1) % C::WIN] = nv;
-            *reinterpret_cast<float4*>(dst + j * C::VP) = s;
-        }
+        if (rows_in) vertical_box_sums<MH, true>(src + (unsigned)(y0 - MH) * pitch, pitch, 0, 0, mode, dst, C::VP);
+        else vertical_box_sums<MH, false>(src, pitch, y0 - MH, h, mode, dst, C::VP);
     }
     __syncthreads();
 
@@ -143,19 +180,19 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a
         R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
     }
     if (a.flow || a.Mout) {
+        float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
+        float* Mo = a.Mout ? a.Mout + (size_t)p * a.m_stride : nullptr;
 #pragma unroll 2
         for (int i = 0; i < 16; ++i) {
             const int r = wid * 4 + (i >> 2), cx = (i & 3) * 32 + lane;
             const int x = x0 + cx, y = y0 + r;
             if (x < w && y < h) {
                 const float2 f = F[r * kFbTW + cx];
-                if (a.flow) a.flow[(size_t)p * a.flow_stride + (size_t)y * a.flow_pitch + x] = f;
-                if (a.Mout) {
+                if (fo) fo[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x] = f;
+                if (Mo) {
                     float mm[5];
-                    update_px(R0, R1, a.plane_stride, pitch, w, h, x, y, f.x, f.y, mm);
-                    float* Mo = a.Mout + (size_t)p * a.m_stride + (size_t)y * pitch + x;
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) Mo[c * a.plane_stride] = mm[c];
+                    update_px(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
+                    store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, mm);
                 }
             }
         }
@@ -197,10 +234,12 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline bool blur_solve_fast_supported(const WinCoef& wc, int pitch) {
     return !wc.gauss && wc.m == 7 && (pitch % 4) == 0;
 }
+// + the image width must be a multiple of 4 (float4 columns are all-inside or all-outside) and at least one chunk
+inline bool blur_solve_fast_shape(int w) { return (w % 4) == 0 && w >= 4; }
 inline int blur_solve_fast_ncta(int w, int h) { return ((w + kFbTW - 1) / kFbTW) * ((h + kFbTH - 1) / kFbTH); }
 
 inline bool blur_solve_fast_aligned(const BlurSolveArgs& a) {
-    return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0;
+    return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0 && blur_solve_fast_shape(a.w);
 }
 
 inline void launch_blur_solve_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {

@@ -203,39 +203,49 @@ __device__ __forceinline__ float border_w(int i, int n) {
     return s;
 }
 
+// Addressing: `plane` and `pitch` are 32-bit element counts and every pointer is formed as base + c*plane + offset
+// with an unsigned 32-bit offset, which ptxas turns into one IMAD.WIDE per pair of loads (a 64-bit size_t
+// formulation costs ~55 integer instructions per pixel here; measured with ncu, see profiles/).
 __device__ __forceinline__ void update_px(const float* __restrict__ R0, const float* __restrict__ R1,
-                                          size_t plane_stride, int pitch, int w, int h, int x, int y,
+                                          unsigned plane, unsigned pitch, int w, int h, int x, int y,
                                           float dx, float dy, float out[5]) {
-    const size_t o = (size_t)y * pitch + x;
+    const unsigned o = (unsigned)y * pitch + (unsigned)x;
+    float q[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) q[c] = __ldg(R0 + (size_t)c * plane + o);
     float fx = (float)x + dx, fy = (float)y + dy;
     const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
     fx -= (float)x1;
     fy -= (float)y1;
     float r2, r3, r4, r5, r6;
-    const float q0 = R0[o], q1 = R0[plane_stride + o], q2 = R0[2 * plane_stride + o],
-                q3 = R0[3 * plane_stride + o], q4 = R0[4 * plane_stride + o];
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const float* p = R1 + (size_t)y1 * pitch + x1;
-        float rw[5];
+        const unsigned o1 = (unsigned)y1 * pitch + (unsigned)x1;
+        const unsigned o2 = o1 + pitch;
+        float t0[5], t1[5], b0[5], b1[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-            const float* pc = p + c * plane_stride;
-            rw[c] = a00 * pc[0] + a01 * pc[1] + a10 * pc[pitch] + a11 * pc[pitch + 1];
+            const float* pa = R1 + (size_t)c * plane + o1;
+            const float* pb = R1 + (size_t)c * plane + o2;
+            t0[c] = __ldg(pa); t1[c] = __ldg(pa + 1);
+            b0[c] = __ldg(pb); b1[c] = __ldg(pb + 1);
         }
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        float rw[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) rw[c] = a00 * t0[c] + a01 * t1[c] + a10 * b0[c] + a11 * b1[c];
         r2 = rw[0];
         r3 = rw[1];
-        r4 = (q2 + rw[2]) * 0.5f;
-        r5 = (q3 + rw[3]) * 0.5f;
-        r6 = (q4 + rw[4]) * 0.25f;
+        r4 = (q[2] + rw[2]) * 0.5f;
+        r5 = (q[3] + rw[3]) * 0.5f;
+        r6 = (q[4] + rw[4]) * 0.25f;
     } else {
         r2 = r3 = 0.f;
-        r4 = q2;
-        r5 = q3;
-        r6 = q4 * 0.5f;
+        r4 = q[2];
+        r5 = q[3];
+        r6 = q[4] * 0.5f;
     }
-    r2 = (q0 - r2) * 0.5f;
-    r3 = (q1 - r3) * 0.5f;
+    r2 = (q[0] - r2) * 0.5f;
+    r3 = (q[1] - r3) * 0.5f;
     r2 += r4 * dy + r6 * dx;
     r3 += r6 * dy + r5 * dx;
     if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
@@ -247,6 +257,11 @@ __device__ __forceinline__ void update_px(const float* __restrict__ R0, const fl
     out[2] = r5 * r5 + r6 * r6;
     out[3] = r4 * r2 + r6 * r3;
     out[4] = r6 * r2 + r5 * r3;
+}
+
+__device__ __forceinline__ void store_m(float* __restrict__ M, unsigned plane, unsigned o, const float m[5]) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) M[(size_t)c * plane + o] = m[c];
 }
 
 struct ResizeTab {
@@ -295,10 +310,8 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     const float* R0 = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
     const float* R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
     float m[5];
-    update_px(R0, R1, a.plane_stride, a.pitch, a.w, a.h, x, y, fl.x, fl.y, m);
-    float* M = a.M + (size_t)p * a.m_stride + (size_t)y * a.pitch + x;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) M[c * a.plane_stride] = m[c];
+    update_px(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, a.w, a.h, x, y, fl.x, fl.y, m);
+    store_m(a.M + (size_t)p * a.m_stride, (unsigned)a.plane_stride, (unsigned)y * (unsigned)a.pitch + (unsigned)x, m);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -432,10 +445,8 @@ __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs 
             const float* R0 = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
             const float* R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
             float mm[5];
-            update_px(R0, R1, a.plane_stride, a.pitch, w, h, x, y, fl.x, fl.y, mm);
-            float* Mo = a.Mout + (size_t)p * a.m_stride + (size_t)y * a.pitch + x;
-#pragma unroll
-            for (int c = 0; c < 5; ++c) Mo[c * a.plane_stride] = mm[c];
+            update_px(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, w, h, x, y, fl.x, fl.y, mm);
+            store_m(a.Mout + (size_t)p * a.m_stride, (unsigned)a.plane_stride, (unsigned)y * (unsigned)a.pitch + (unsigned)x, mm);
         }
     }
     if (a.partial) roi_reduce_store(a, p, x, y, valid, fl, s_red);
