@@ -15,6 +15,7 @@
 
 #include "farneback_kernels.cuh"
 #include "farneback_fast.cuh"
+#include "farneback_march.cuh"
 #include "pc1_kernels.cuh"
 
 namespace {
@@ -291,23 +292,50 @@ int launch_update(const bf::UpdateArgs& a, int np, cudaStream_t st) {
     return 0;
 }
 
-bool use_fast_blur(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, bool allow_fast) {
-    return allow_fast && bf::blur_solve_fast_supported(wc, a.pitch) && bf::blur_solve_fast_aligned(a);
+// Which kernel runs one blur+solve(+update) iteration: the warp-specialised strip-marching kernel (default), the
+// tile kernel (BTCSFLOW_KERNEL=tile), or the runtime-parameter kernel (BTCSFLOW_NO_FAST=1 / unsupported parameters).
+enum BlurKernel { BK_GENERIC = 0, BK_TILE = 1, BK_MARCH = 2 };
+
+int sm_count_cached() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
-int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, bool allow_fast) {
-    if (use_fast_blur(a, wc, allow_fast)) return bf::blur_solve_fast_ncta(a.w, a.h);
-    return cdiv(a.w, bf::kBsTW) * cdiv(a.h, bf::kBsTH);
+BlurKernel choose_blur_kernel(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, bool allow_fast) {
+    if (!allow_fast) return BK_GENERIC;
+    const char* e = getenv("BTCSFLOW_KERNEL");                      // read per call: tests flip it within a process
+    const int pref = (e && strcmp(e, "tile") == 0) ? BK_TILE : BK_MARCH;
+    if (pref == BK_MARCH && bf::march_supported(wc, a)) return BK_MARCH;
+    if (bf::blur_solve_fast_supported(wc, a.pitch) && bf::blur_solve_fast_aligned(a)) return BK_TILE;
+    return BK_GENERIC;
+}
+
+int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast) {
+    switch (choose_blur_kernel(a, wc, allow_fast)) {
+        case BK_MARCH: return bf::march_ncta(a.w, a.h, np, sm_count_cached());
+        case BK_TILE: return bf::blur_solve_fast_ncta(a.w, a.h);
+        default: return cdiv(a.w, bf::kBsTW) * cdiv(a.h, bf::kBsTH);
+    }
 }
 
 int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast, cudaStream_t st) {
-    if (use_fast_blur(a, wc, allow_fast)) {
-        bf::launch_blur_solve_fast(a, wc, np, st);
-        LAUNCH_CHECK();
-        return 0;
+    switch (choose_blur_kernel(a, wc, allow_fast)) {
+        case BK_MARCH:
+            bf::launch_march(a, wc, np, sm_count_cached(), st);
+            break;
+        case BK_TILE:
+            bf::launch_blur_solve_fast(a, wc, np, st);
+            break;
+        default: {
+            dim3 g(cdiv(a.w, bf::kBsTW), cdiv(a.h, bf::kBsTH), np);
+            bf::k_blur_solve_generic<<<g, 256, 0, st>>>(a, wc);
+        }
     }
-    dim3 g(cdiv(a.w, bf::kBsTW), cdiv(a.h, bf::kBsTH), np);
-    bf::k_blur_solve_generic<<<g, 256, 0, st>>>(a, wc);
     LAUNCH_CHECK();
     return 0;
 }
@@ -423,7 +451,7 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
                 p->prof_pairs += np;
             }
             if (last && finest && want_roi) {
-                const int ncta = blur_solve_ncta(a, p->wc, p->use_fast);
+                const int ncta = blur_solve_ncta(a, p->wc, np, p->use_fast);
                 bf::k_roi_finalize<<<cdiv(np * roi->n_roi, 4), 128, 0, st>>>(p->partial, np, roi->n_roi, ncta, roi->ex,
                                                                              roi->ey, t0 + 1, roi->out, roi->T);
                 LAUNCH_CHECK();
@@ -544,7 +572,8 @@ int bf_plan_create(const bf_params* params, int width, int height, int max_pairs
         cudaMemset(p->M[i], 0, m_elems * sizeof(float));
     }
     if ((rc = plan_alloc(p, &p->axes, (size_t)p->B * 4))) return cleanup_fail(rc);
-    p->ncta_max = std::max(cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), bf::blur_solve_fast_ncta(fine.w, fine.h));
+    p->ncta_max = std::max({cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), bf::blur_solve_fast_ncta(fine.w, fine.h),
+                            cdiv(fine.w, bf::kFbTW) * 16});
     if ((rc = plan_alloc(p, &p->partial, (size_t)p->B * std::max(max_rois, 1) * p->ncta_max * bf::kRoiVals))) return cleanup_fail(rc);
     const char* nofast = getenv("BTCSFLOW_NO_FAST");
     p->use_fast = !(nofast && nofast[0] == '1');

@@ -97,20 +97,27 @@ def test_torch_tensors_stay_on_device():
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
 
 
-def test_generic_and_fast_kernels_agree(monkeypatch):
-    """BTCSFLOW_NO_FAST=1 forces the runtime-parameter kernels; both must sit inside the tight gate."""
+def test_all_kernel_variants_agree(monkeypatch):
+    """The same parameters through the three implementations of the iteration kernel -- warp-specialised
+    strip-marching (default), tile (BTCSFLOW_KERNEL=tile), runtime-parameter (BTCSFLOW_NO_FAST=1) -- all inside the
+    tight gate against cv2 and within float rounding of each other."""
     import btcs_pnes_optical_flow_b200 as B
     from oracle import cv2_ref
-    a, b = textured(270, 480, 1), textured(270, 480, 1, shift=(1.7, -0.8))
-    for p in (B.FB_PARAMS, dict(B.FB_PARAMS, levels=5, winsize=21, poly_n=7, poly_sigma=1.5, flags=256)):
-        ref = cv2_ref.farneback(a, b, **p)
-        fast = B.FlowPlan(480, 270, p).flow_pair(a, b)
-        monkeypatch.setenv("BTCSFLOW_NO_FAST", "1")
-        slow = B.FlowPlan(480, 270, p).flow_pair(a, b)
-        monkeypatch.delenv("BTCSFLOW_NO_FAST")
-        for f in (fast, slow):
-            mean, mx = epe(f, ref)
-            assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (mean, mx)
+    for (h, w) in ((270, 480), (203, 316)):
+        a, b = textured(h, w, 1), textured(h, w, 1, shift=(1.7, -0.8))
+        for p in (B.FB_PARAMS, dict(B.FB_PARAMS, levels=5, winsize=21, poly_n=7, poly_sigma=1.5, flags=256)):
+            ref = cv2_ref.farneback(a, b, **p)
+            outs = {}
+            for name, env in (("march", {}), ("tile", {"BTCSFLOW_KERNEL": "tile"}), ("generic", {"BTCSFLOW_NO_FAST": "1"})):
+                for k, v in env.items():
+                    monkeypatch.setenv(k, v)
+                with B.FlowPlan(w, h, p) as plan:
+                    outs[name] = plan.flow_pair(a, b)
+                for k in env:
+                    monkeypatch.delenv(k)
+                mean, mx = epe(outs[name], ref)
+                assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (name, h, w, mean, mx)
+            assert epe(outs["march"], outs["generic"])[1] < 1e-3 and epe(outs["tile"], outs["generic"])[1] < 1e-3
 
 
 def test_1080p_full_size_properties():
