@@ -10,6 +10,7 @@ OPTFLOW_USE_INITIAL_FLOW = 4
 OPTFLOW_FARNEBACK_GAUSSIAN = 256
 BF_E_INVALID, BF_E_UNSUPPORTED, BF_E_NODEVICE = -1, -2, -3
 BF_DTYPE_U8, BF_DTYPE_F32 = 0, 1
+BF_PLAN_EXACT_F32 = 1
 
 
 class BfParams(C.Structure):
@@ -43,7 +44,9 @@ class Cv2CompatError(ValueError, BtcsFlowError):
 _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
 _SIGNATURES = {
     "bf_plan_create": (_i, [C.POINTER(BfParams), _i, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "bf_plan_create_ex": (_i, [C.POINTER(BfParams), _i, _i, _i, _i, _i, C.c_uint, C.POINTER(_vp)]),
     "bf_plan_destroy": (_i, [_vp]),
+    "bf_plan_coeff_storage": (_i, [_vp]),
     "bf_plan_workspace_bytes": (_sz, [_vp]),
     "bf_plan_num_scales": (_i, [_vp]),
     "bf_plan_scale_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_d), C.POINTER(_i)]),

@@ -181,7 +181,7 @@ struct ScaleInfo {
     int *fix = nullptr, *fiy = nullptr;     // flow upsample: next-coarser scale -> this scale
     float *fax = nullptr, *fay = nullptr;
     float* I = nullptr;                       // [F][h][pitch]
-    float* R = nullptr;                       // [F][5][h][pitch]
+    void* R = nullptr;                        // fp32 planes [F][5][h][pitch], or packed fp16 pixels [F][h][pitch] x 16 B
     float2* flow = nullptr;                   // [B][h][pitch]
 };
 
@@ -209,12 +209,16 @@ struct bf_plan {
     // host-staging path
     uint8_t* stage[2] = {nullptr, nullptr};
     float* stage_flow = nullptr;
+    uint8_t* pair_in[2] = {nullptr, nullptr};   // bf_flow_pair_host staging (H x W x 4 bytes each)
+    float* pair_flow = nullptr;
     double* d_ex = nullptr; double* d_ey = nullptr; int axes_cap = 0;
     uint8_t* d_masks = nullptr; size_t masks_cap = 0;
     float* d_out = nullptr; size_t out_cap = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool use_fast = true;
+    bool r_half = false;        // polynomial coefficients stored as 8 x fp16 per pixel (fast path, uint8 input)
+    int sm_count = 148;
     // dominant-kernel timing (bf_plan_profile)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
@@ -269,31 +273,33 @@ int launch_pyramid(bf_plan* p, const ScaleInfo& s, const T* src, size_t pitch_by
     return 0;
 }
 
-int launch_polyexp(bf_plan* p, const float* I, int pitch, size_t frame_stride, int w, int h, float* R,
-                   size_t plane_stride, size_t slot_stride, int slot0, int nslots, int nf, const bf::PolyCoef& pc,
-                   bool allow_fast, cudaStream_t st) {
+int launch_polyexp(const float* I, int pitch, size_t frame_stride, int w, int h, void* R, size_t plane_stride,
+                   size_t slot_stride, int slot0, int nslots, int nf, const bf::PolyCoef& pc, bool allow_fast, bool r_half,
+                   cudaStream_t st) {
     if (allow_fast && bf::polyexp_fast_supported(pc.n, pitch) && bf::polyexp_fast_aligned(R, plane_stride, slot_stride)) {
-        bf::launch_polyexp_fast(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
+        bf::launch_polyexp_fast(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, r_half, st);
         LAUNCH_CHECK();
         return 0;
     }
+    if (r_half) return fail(BF_E_UNSUPPORTED, "internal: packed R needs the compile-time polyexp kernel");
     dim3 g(cdiv(w, bf::kPeTW), cdiv(h, bf::kPeTH), nf);
-    bf::k_polyexp_generic<<<g, 256, 0, st>>>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0,
-                                             nslots, pc);
+    bf::k_polyexp_generic<<<g, 256, 0, st>>>(I, pitch, frame_stride, w, h, static_cast<float*>(R), plane_stride, slot_stride,
+                                             slot0, nslots, pc);
     LAUNCH_CHECK();
     return 0;
 }
 
-int launch_update(const bf::UpdateArgs& a, int np, cudaStream_t st) {
+int launch_update(const bf::UpdateArgs& a, int np, bool r_half, cudaStream_t st) {
     dim3 b(64, 4);
     dim3 g(cdiv(a.w, 64), cdiv(a.h, 4), np);
-    bf::k_update<<<g, b, 0, st>>>(a);
+    if (r_half) bf::k_update<true><<<g, b, 0, st>>>(a);
+    else bf::k_update<false><<<g, b, 0, st>>>(a);
     LAUNCH_CHECK();
     return 0;
 }
 
-// Which kernel runs one blur+solve(+update) iteration: the warp-specialised strip-marching kernel (default), the
-// tile kernel (BTCSFLOW_KERNEL=tile), or the runtime-parameter kernel (BTCSFLOW_NO_FAST=1 / unsupported parameters).
+// Which kernel runs one blur+solve(+update) iteration: the tile kernel (default), the warp-specialised strip-marching
+// kernel (BTCSFLOW_KERNEL=march), or the runtime-parameter kernel (BTCSFLOW_NO_FAST=1 / unsupported parameters).
 enum BlurKernel { BK_GENERIC = 0, BK_TILE = 1, BK_MARCH = 2 };
 
 int sm_count_cached() {
@@ -309,7 +315,7 @@ int sm_count_cached() {
 BlurKernel choose_blur_kernel(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, bool allow_fast) {
     if (!allow_fast) return BK_GENERIC;
     const char* e = getenv("BTCSFLOW_KERNEL");                      // read per call: tests flip it within a process
-    const int pref = (e && strcmp(e, "tile") == 0) ? BK_TILE : BK_MARCH;
+    const int pref = (e && strcmp(e, "march") == 0) ? BK_MARCH : BK_TILE;   // tile kernel measured faster (profiles/)
     if (pref == BK_MARCH && bf::march_supported(wc, a)) return BK_MARCH;
     if (bf::blur_solve_fast_supported(wc, a.pitch) && bf::blur_solve_fast_aligned(a)) return BK_TILE;
     return BK_GENERIC;
@@ -323,17 +329,19 @@ int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, b
     }
 }
 
-int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast, cudaStream_t st) {
+int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast, bool r_half,
+                      cudaStream_t st) {
     switch (choose_blur_kernel(a, wc, allow_fast)) {
         case BK_MARCH:
-            bf::launch_march(a, wc, np, sm_count_cached(), st);
+            bf::launch_march(a, wc, np, sm_count_cached(), r_half, st);
             break;
         case BK_TILE:
-            bf::launch_blur_solve_fast(a, wc, np, st);
+            bf::launch_blur_solve_fast(a, wc, np, r_half, st);
             break;
         default: {
             dim3 g(cdiv(a.w, bf::kBsTW), cdiv(a.h, bf::kBsTH), np);
-            bf::k_blur_solve_generic<<<g, 256, 0, st>>>(a, wc);
+            if (r_half) bf::k_blur_solve_generic<true><<<g, 256, 0, st>>>(a, wc);
+            else bf::k_blur_solve_generic<false><<<g, 256, 0, st>>>(a, wc);
         }
     }
     LAUNCH_CHECK();
@@ -347,8 +355,8 @@ int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_
     for (auto& s : p->sc) {
         int rc = launch_pyramid<T>(p, s, frames, pitch_bytes, frame_bytes, nf, s.I, s.pitch, s.plane, st);
         if (rc) return rc;
-        rc = launch_polyexp(p, s.I, s.pitch, s.plane, s.w, s.h, s.R, s.plane, 5 * s.plane, tf % p->F, p->F, nf,
-                            p->pc, p->use_fast, st);
+        rc = launch_polyexp(s.I, s.pitch, s.plane, s.w, s.h, s.R, s.plane, p->r_half ? s.plane : 5 * s.plane, tf % p->F,
+                            p->F, nf, p->pc, p->use_fast, p->r_half, st);
         if (rc) return rc;
     }
     return 0;
@@ -400,7 +408,7 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
         const bool finest = (i == nsc - 1);
         const size_t m_stride = 5 * s.plane;
         bf::UpdateArgs u{};
-        u.R = s.R; u.plane_stride = s.plane; u.slot_stride = 5 * s.plane; u.slot0 = slot0; u.nslots = p->F;
+        u.R = s.R; u.plane_stride = s.plane; u.slot_stride = p->r_half ? s.plane : 5 * s.plane; u.slot0 = slot0; u.nslots = p->F;
         u.pitch = s.pitch; u.w = s.w; u.h = s.h;
         if (i == 0) {
             u.flow_mode = 0;
@@ -412,13 +420,13 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
             u.tab = bf::ResizeTab{s.fix, s.fax, s.fiy, s.fay};
         }
         u.M = p->M[0]; u.m_stride = m_stride;
-        int rc = launch_update(u, np, st);
+        int rc = launch_update(u, np, p->r_half, st);
         if (rc) return rc;
         for (int it = 0; it < I; ++it) {
             const bool last = (it == I - 1);
             bf::BlurSolveArgs a{};
             a.M = p->M[it & 1]; a.m_stride = m_stride; a.plane_stride = s.plane; a.pitch = s.pitch; a.w = s.w; a.h = s.h;
-            a.R = s.R; a.slot_stride = 5 * s.plane; a.slot0 = slot0; a.nslots = p->F;
+            a.R = s.R; a.slot_stride = p->r_half ? s.plane : 5 * s.plane; a.slot0 = slot0; a.nslots = p->F;
             if (!last) {
                 a.Mout = p->M[(it + 1) & 1];
             } else if (!finest) {
@@ -443,7 +451,7 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
                 }
                 CU(cudaEventRecord(p->prof_ev[p->prof_used], st));
             }
-            rc = launch_blur_solve(a, p->wc, np, p->use_fast, st);
+            rc = launch_blur_solve(a, p->wc, np, p->use_fast, p->r_half, st);
             if (rc) return rc;
             if (prof) {
                 CU(cudaEventRecord(p->prof_ev[p->prof_used + 1], st));
@@ -491,6 +499,11 @@ int bf_device_sm(int device) {
 
 int bf_plan_create(const bf_params* params, int width, int height, int max_pairs, int max_rois, int device,
                    bf_plan** out) {
+    return bf_plan_create_ex(params, width, height, max_pairs, max_rois, device, 0, out);
+}
+
+int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pairs, int max_rois, int device,
+                      unsigned flags, bf_plan** out) {
     if (!out) return fail(BF_E_INVALID, "out is NULL");
     *out = nullptr;
     int rc = validate_params(params, width, height);
@@ -512,6 +525,15 @@ int bf_plan_create(const bf_params* params, int width, int height, int max_pairs
         return fail(BF_E_INVALID, "singular moment matrix for poly_n=%d poly_sigma=%g", params->poly_n, params->poly_sigma);
     }
     make_win_coef(params->winsize, params->flags, p->wc);
+    {
+        const char* nofast = getenv("BTCSFLOW_NO_FAST");
+        p->use_fast = !(nofast && nofast[0] == '1');
+        const char* rs = getenv("BTCSFLOW_R_STORAGE");
+        const bool want_f32 = (flags & BF_PLAN_EXACT_F32) || (rs && strcmp(rs, "f32") == 0);
+        // packed fp16 coefficients need the compile-time polyexp kernels (poly_n 5 / 7) and bounded (uint8) input
+        p->r_half = p->use_fast && !want_f32 && (params->poly_n == 5 || params->poly_n == 7);
+        cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    }
 
     // scale selection
     int k = 0;
@@ -553,11 +575,16 @@ int bf_plan_create(const bf_params* params, int width, int height, int max_pairs
             if (upload(idx, &s.fiy) != cudaSuccess || upload(wgt, &s.fay) != cudaSuccess) return cleanup_fail(fail(2, "table upload failed"));
         }
         if ((rc = plan_alloc(p, &s.I, (size_t)p->F * s.plane))) return cleanup_fail(rc);
-        if ((rc = plan_alloc(p, &s.R, (size_t)p->F * 5 * s.plane))) return cleanup_fail(rc);
+        {
+            uint8_t* rbuf = nullptr;
+            const size_t rbytes = (size_t)p->F * s.plane * (p->r_half ? sizeof(uint4) : 5 * sizeof(float));
+            if ((rc = plan_alloc(p, &rbuf, rbytes))) return cleanup_fail(rc);
+            cudaMemset(rbuf, 0, rbytes);
+            s.R = rbuf;
+        }
         if ((rc = plan_alloc(p, &s.flow, (size_t)p->B * s.plane))) return cleanup_fail(rc);
         // rows [h, pitch) padding must hold finite values for vectorised kernels: zero everything once
         cudaMemset(s.I, 0, (size_t)p->F * s.plane * sizeof(float));
-        cudaMemset(s.R, 0, (size_t)p->F * 5 * s.plane * sizeof(float));
         cudaMemset(s.flow, 0, (size_t)p->B * s.plane * sizeof(float2));
     }
     const ScaleInfo& fine = p->sc.back();
@@ -575,8 +602,6 @@ int bf_plan_create(const bf_params* params, int width, int height, int max_pairs
     p->ncta_max = std::max({cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), bf::blur_solve_fast_ncta(fine.w, fine.h),
                             cdiv(fine.w, bf::kFbTW) * 16});
     if ((rc = plan_alloc(p, &p->partial, (size_t)p->B * std::max(max_rois, 1) * p->ncta_max * bf::kRoiVals))) return cleanup_fail(rc);
-    const char* nofast = getenv("BTCSFLOW_NO_FAST");
-    p->use_fast = !(nofast && nofast[0] == '1');
     if (cudaDeviceSynchronize() != cudaSuccess) return cleanup_fail(fail(2, "plan initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out = p;
     return 0;
@@ -592,6 +617,7 @@ int bf_plan_destroy(bf_plan* p) {
     }
     cudaFree(p->tmp); cudaFree(p->M[0]); cudaFree(p->M[1]); cudaFree(p->axes); cudaFree(p->partial);
     cudaFree(p->stage[0]); cudaFree(p->stage[1]); cudaFree(p->stage_flow);
+    cudaFree(p->pair_in[0]); cudaFree(p->pair_in[1]); cudaFree(p->pair_flow);
     cudaFree(p->d_ex); cudaFree(p->d_ey); cudaFree(p->d_masks); cudaFree(p->d_out);
     for (int i = 0; i < 2; ++i) {
         if (p->ev_copied[i]) cudaEventDestroy(p->ev_copied[i]);
@@ -631,6 +657,7 @@ int bf_plan_profile_read(bf_plan* p, int* n_launches, double* total_ms, long lon
 
 size_t bf_plan_workspace_bytes(const bf_plan* p) { return p ? p->bytes : 0; }
 int bf_plan_num_scales(const bf_plan* p) { return p ? (int)p->sc.size() : BF_E_INVALID; }
+int bf_plan_coeff_storage(const bf_plan* p) { return p ? (p->r_half ? 16 : 32) : BF_E_INVALID; }
 
 int bf_plan_scale_info(const bf_plan* p, int i, int* w, int* h, int* ksize, double* sigma, int* pitch) {
     int rc = check_plan(p);
@@ -653,6 +680,9 @@ int bf_flow_pair(bf_plan* p, const void* prev, const void* next, int dtype, size
     if (dtype != BF_DTYPE_U8 && dtype != BF_DTYPE_F32) return fail(BF_E_INVALID, "dtype must be BF_DTYPE_U8 or BF_DTYPE_F32");
     const size_t esz = dtype == BF_DTYPE_U8 ? 1 : 4;
     if (pitch_bytes < (size_t)p->W * esz) return fail(BF_E_INVALID, "pitch_bytes smaller than a row");
+    if (dtype == BF_DTYPE_F32 && p->r_half)
+        return fail(BF_E_UNSUPPORTED, "float32 input needs a plan created with BF_PLAN_EXACT_F32 (fp16 coefficient storage "
+                                      "is only range-safe for uint8 frames)");
     DeviceGuard dg(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const void* fr[2] = {prev, next};
@@ -672,23 +702,22 @@ int bf_flow_pair_host(bf_plan* p, const void* prev, const void* next, int dtype,
     if (dtype != BF_DTYPE_U8 && dtype != BF_DTYPE_F32) return fail(BF_E_INVALID, "dtype must be BF_DTYPE_U8 or BF_DTYPE_F32");
     DeviceGuard dg(p->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t img_bytes = pitch_bytes * p->H;
+    const size_t esz = dtype == BF_DTYPE_U8 ? 1 : 4;
+    if (pitch_bytes < (size_t)p->W * esz) return fail(BF_E_INVALID, "pitch_bytes smaller than a row");
+    const size_t row_bytes = (size_t)p->W * esz;
     const size_t flow_bytes = (size_t)p->H * p->W * sizeof(float2);
-    void *d0 = nullptr, *d1 = nullptr, *df = nullptr;
-    CU(cudaMallocAsync(&d0, img_bytes, st));
-    CU(cudaMallocAsync(&d1, img_bytes, st));
-    CU(cudaMallocAsync(&df, flow_bytes, st));
-    CU(cudaMemcpyAsync(d0, prev, img_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d1, next, img_bytes, cudaMemcpyHostToDevice, st));
-    rc = bf_flow_pair(p, d0, d1, dtype, pitch_bytes, (float*)df, stream);
-    if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(flow_out, df, flow_bytes, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) rc = fail((int)e, "D2H copy failed: %s", cudaGetErrorString(e));
+    if (!p->pair_flow) {                         // plan-owned staging: no allocation on the per-pair hot path
+        for (int i = 0; i < 2; ++i)
+            if ((rc = plan_alloc(p, &p->pair_in[i], (size_t)p->H * p->W * 4))) return rc;
+        if ((rc = plan_alloc(p, &p->pair_flow, (size_t)p->H * p->W * 2))) return rc;
     }
-    cudaFreeAsync(d0, st); cudaFreeAsync(d1, st); cudaFreeAsync(df, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (!rc && e != cudaSuccess) rc = fail((int)e, "stream sync failed: %s", cudaGetErrorString(e));
-    return rc;
+    CU(cudaMemcpy2DAsync(p->pair_in[0], row_bytes, prev, pitch_bytes, row_bytes, p->H, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpy2DAsync(p->pair_in[1], row_bytes, next, pitch_bytes, row_bytes, p->H, cudaMemcpyHostToDevice, st));
+    rc = bf_flow_pair(p, p->pair_in[0], p->pair_in[1], dtype, row_bytes, p->pair_flow, stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(flow_out, p->pair_flow, flow_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int bf_flow_series(bf_plan* p, const uint8_t* frames, int T, const double* ex, const double* ey,
@@ -819,13 +848,24 @@ int bf_pc1_sliding_batched(const double* vx, const double* vy, int n_series, int
         Kmax = std::max(Kmax, K);
     }
     const size_t nw = (size_t)n_series * std::max(Ktot, 1);
-    bf::Pc1Cfg* d_cfg = nullptr;
-    double* d_w = nullptr;  // wx, wy, cwx, cwy
-    int* d_i = nullptr;     // valid, cen, nvalid
-    CU(cudaMallocAsync((void**)&d_cfg, n_cfg * sizeof(bf::Pc1Cfg), st));
-    CU(cudaMallocAsync((void**)&d_w, 4 * nw * sizeof(double), st));
-    CU(cudaMallocAsync((void**)&d_i, (2 * nw + (size_t)n_series * n_cfg) * sizeof(int), st));
-    // pageable source: the copy is staged before the call returns, so the vector may die afterwards
+    // Grow-only per-thread scratch: cudaMallocAsync/cudaFreeAsync would hand the memory back to the OS at every
+    // synchronisation (default pool release threshold 0) and cost milliseconds per call on a KB-sized problem.
+    struct Scratch { void* buf = nullptr; size_t cap = 0; int dev = -1; };
+    static thread_local Scratch sc;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const size_t cfg_bytes = round_up(n_cfg * (int)sizeof(bf::Pc1Cfg), 256);
+    const size_t need = cfg_bytes + 4 * nw * sizeof(double) + (2 * nw + (size_t)n_series * n_cfg) * sizeof(int);
+    if (sc.dev != dev || sc.cap < need) {
+        if (sc.buf) { CU(cudaDeviceSynchronize()); cudaFree(sc.buf); sc.buf = nullptr; sc.cap = 0; }
+        CU(cudaMalloc(&sc.buf, need + need / 2));
+        sc.cap = need + need / 2;
+        sc.dev = dev;
+    }
+    bf::Pc1Cfg* d_cfg = reinterpret_cast<bf::Pc1Cfg*>(sc.buf);
+    double* d_w = reinterpret_cast<double*>(static_cast<char*>(sc.buf) + cfg_bytes);   // wx, wy, cwx, cwy
+    int* d_i = reinterpret_cast<int*>(d_w + 4 * nw);                                   // valid, cen, nvalid
+    // pageable source: staged before the call returns, so the vector may die afterwards
     CU(cudaMemcpyAsync(d_cfg, cfgs.data(), n_cfg * sizeof(bf::Pc1Cfg), cudaMemcpyHostToDevice, st));
     double *wx = d_w, *wy = d_w + nw, *cwx = d_w + 2 * nw, *cwy = d_w + 3 * nw;
     int *valid = d_i, *cen = d_i + nw, *nvalid = d_i + 2 * nw;
@@ -840,9 +880,6 @@ int bf_pc1_sliding_batched(const double* vx, const double* vy, int n_series, int
     dim3 gC(cdiv(n, 256), n_series, n_cfg);
     bf::k_pc1_project<<<gC, 256, 0, st>>>(vx, vy, n_series, n, d_cfg, n_cfg, Ktot, cwx, cwy, cen, nvalid, pc1_out);
     LAUNCH_CHECK();
-    CU(cudaFreeAsync(d_cfg, st));
-    CU(cudaFreeAsync(d_w, st));
-    CU(cudaFreeAsync(d_i, st));
     return 0;
 }
 
@@ -898,8 +935,8 @@ int bf_stage_poly_exp(const float* image, int w, int h, int poly_n, double poly_
     if (!make_poly_coef(poly_n, poly_sigma, pc)) return fail(BF_E_INVALID, "singular moment matrix");
     const char* nofast = getenv("BTCSFLOW_NO_FAST");
     const bool fast = !(nofast && nofast[0] == '1');
-    return launch_polyexp(nullptr, image, w, (size_t)w * h, w, h, R_planes, (size_t)w * h, (size_t)5 * w * h, 0, 1, 1, pc,
-                          fast, (cudaStream_t)stream);
+    return launch_polyexp(image, w, (size_t)w * h, w, h, R_planes, (size_t)w * h, (size_t)5 * w * h, 0, 1, 1, pc, fast, false,
+                          (cudaStream_t)stream);
 }
 
 int bf_stage_update_matrices(const float* R0, const float* R1, const float* flow, int w, int h, float* M, void* stream) {
@@ -913,7 +950,7 @@ int bf_stage_update_matrices(const float* R0, const float* R1, const float* flow
     u.pitch = w; u.w = w; u.h = h;
     u.flow_mode = 1; u.flow = (const float2*)flow; u.flow_pitch = w; u.flow_stride = 0;
     u.M = M; u.m_stride = 0;
-    return launch_update(u, 1, (cudaStream_t)stream);
+    return launch_update(u, 1, false, (cudaStream_t)stream);
 }
 
 int bf_stage_blur_solve(const float* M, int w, int h, int winsize, int flags, float* flow, void* stream) {
@@ -926,7 +963,7 @@ int bf_stage_blur_solve(const float* M, int w, int h, int winsize, int flags, fl
     a.flow = (float2*)flow; a.flow_pitch = w; a.flow_stride = 0;
     const char* nofast = getenv("BTCSFLOW_NO_FAST");
     const bool fast = !(nofast && nofast[0] == '1');
-    return launch_blur_solve(a, wc, 1, fast, (cudaStream_t)stream);
+    return launch_blur_solve(a, wc, 1, fast, false, (cudaStream_t)stream);
 }
 
 int bf_stage_upsample_flow(const float* flow_in, int ws, int hs, int w, int h, float mult, float* flow_out, void* stream) {
@@ -936,10 +973,10 @@ int bf_stage_upsample_flow(const float* flow_in, int ws, int hs, int w, int h, f
     resize_table(w, ws, ix, ax);
     resize_table(h, hs, iy, ay);
     int *dix = nullptr, *diy = nullptr; float *dax = nullptr, *day = nullptr;
-    CU(cudaMallocAsync((void**)&dix, w * sizeof(int), st));
-    CU(cudaMallocAsync((void**)&diy, h * sizeof(int), st));
-    CU(cudaMallocAsync((void**)&dax, w * sizeof(float), st));
-    CU(cudaMallocAsync((void**)&day, h * sizeof(float), st));
+    CU(cudaMalloc((void**)&dix, w * sizeof(int)));
+    CU(cudaMalloc((void**)&diy, h * sizeof(int)));
+    CU(cudaMalloc((void**)&dax, w * sizeof(float)));
+    CU(cudaMalloc((void**)&day, h * sizeof(float)));
     CU(cudaMemcpyAsync(dix, ix.data(), w * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(diy, iy.data(), h * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dax, ax.data(), w * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -949,9 +986,9 @@ int bf_stage_upsample_flow(const float* flow_in, int ws, int hs, int w, int h, f
     u.flow = (const float2*)flow_in; u.flow_pitch = ws; u.flow_stride = 0; u.ws = ws; u.hs = hs; u.mult = mult;
     u.tab = bf::ResizeTab{dix, dax, diy, day};
     u.flow_out = (float2*)flow_out; u.flow_out_pitch = w; u.flow_out_stride = 0;
-    int rc = launch_update(u, 1, st);
-    cudaFreeAsync(dix, st); cudaFreeAsync(diy, st); cudaFreeAsync(dax, st); cudaFreeAsync(day, st);
+    int rc = launch_update(u, 1, false, st);
     CU(cudaStreamSynchronize(st));  // the host tables above must outlive the async copies
+    cudaFree(dix); cudaFree(diy); cudaFree(dax); cudaFree(day);
     return rc;
 }
 

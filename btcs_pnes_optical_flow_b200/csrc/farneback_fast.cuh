@@ -76,7 +76,41 @@ __device__ __forceinline__ void vertical_box_sums(const float* __restrict__ src,
     }
 }
 
-template <int MH>
+// Lines of R that a block of rows [ya, ya+nrows) x columns [x0, x0+128) will touch in its update tail: R0 under the
+// block, R1 within +-2 rows / +-32 columns (larger flows simply miss).  Requested into L2 ahead of use.
+template <bool RH>
+__device__ __forceinline__ void prefetch_r_block(const void* R0v, const void* R1v, unsigned plane, unsigned pitch, int w, int h,
+                                                 int x0, int ya, int nrows, int tid, int nthreads) {
+    if (RH) {
+        const uint4* R0 = static_cast<const uint4*>(R0v);
+        const uint4* R1 = static_cast<const uint4*>(R1v);
+        const int xmax = max(w - 1, 0);                                  // 8 pixels per 128-byte line
+        for (int e = tid; e < nrows * 16; e += nthreads) {
+            const int yy = min(ya + (e >> 4), h - 1), xx = min(x0 + (e & 15) * 8, xmax);
+            prefetch_l2(R0 + (unsigned)yy * pitch + (unsigned)xx);
+        }
+        for (int e = tid; e < (nrows + 4) * 24; e += nthreads) {
+            const int yy = min(max(ya - 2 + e / 24, 0), h - 1), xx = min(max(x0 - 32 + (e % 24) * 8, 0), xmax);
+            prefetch_l2(R1 + (unsigned)yy * pitch + (unsigned)xx);
+        }
+    } else {
+        const float* R0 = static_cast<const float*>(R0v);
+        const float* R1 = static_cast<const float*>(R1v);
+        const int xmax = (int)pitch - 32;
+        for (int e = tid; e < 5 * nrows * 4; e += nthreads) {
+            const int c = e / (nrows * 4), rem = e - c * (nrows * 4);
+            const int yy = min(ya + (rem >> 2), h - 1), xx = min(x0 + (rem & 3) * 32, xmax);
+            prefetch_l2(R0 + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
+        }
+        for (int e = tid; e < 5 * (nrows + 4) * 6; e += nthreads) {
+            const int c = e / ((nrows + 4) * 6), rem = e - c * ((nrows + 4) * 6);
+            const int yy = min(max(ya - 2 + rem / 6, 0), h - 1), xx = min(max(x0 - 32 + (rem % 6) * 32, 0), xmax);
+            prefetch_l2(R1 + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
+        }
+    }
+}
+
+template <int MH, bool RH>
 __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a, const float reg) {
     using C = FastBoxCfg<MH>;
     extern __shared__ __align__(16) float smem[];
@@ -89,22 +123,25 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a
     const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
     const float* Mp = a.M + (size_t)p * a.m_stride;
 
-    // L2 prefetch of what phase 3 will read (R0 under the tile, R1 around it): the lines travel from HBM while
-    // phases 1-2 run, so the gather later pays L2 latency instead of DRAM latency.
+    // A lone CTA of this kernel takes ~22 us (ncu, profiles/): its time is a chain of HBM round trips, not bandwidth.
+    // So the whole M tile (with halo) is requested into L2 up front -- phase 1's register-window stream then pays L2
+    // latency per step -- and likewise what phase 3 will read (R0 under the tile, R1 around it), which travels from
+    // HBM while phases 1-2 run.
+    {
+        const int xlo = max(x0 - C::HALO, 0) & ~31, xhi = min(x0 + kFbTW + C::HALO, w);
+        const int nline = (xhi - xlo + 31) / 32, nrow = kFbTH + 2 * MH;
+        for (int e = tid; e < 5 * nrow * nline; e += 256) {
+            const int c = e / (nrow * nline), rem = e - c * (nrow * nline);
+            const int yy = min(max(y0 - MH + rem / nline, 0), h - 1), xx = xlo + (rem % nline) * 32;
+            prefetch_l2(Mp + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
+        }
+    }
+    const void* R0 = nullptr;
+    const void* R1 = nullptr;
     if (a.Mout) {
-        const float* R0p = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
-        const float* R1p = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
-        const int xmax = (int)pitch - 32;
-        for (int e = tid; e < 5 * kFbTH * 4; e += 256) {
-            const int c = e / (kFbTH * 4), rem = e - c * (kFbTH * 4);
-            const int yy = min(y0 + (rem >> 2), h - 1), xx = min(x0 + (rem & 3) * 32, xmax);
-            prefetch_l2(R0p + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
-        }
-        for (int e = tid; e < 5 * (kFbTH + 4) * 6; e += 256) {
-            const int c = e / ((kFbTH + 4) * 6), rem = e - c * ((kFbTH + 4) * 6);
-            const int yy = min(max(y0 - 2 + rem / 6, 0), h - 1), xx = min(max(x0 - 32 + (rem % 6) * 32, 0), xmax);
-            prefetch_l2(R1p + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
-        }
+        R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
+        R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
+        prefetch_r_block<RH>(R0, R1, plane, pitch, w, h, x0, y0, kFbTH, tid, 256);
     }
 
     // ---------------- phase 1: vertical sums ----------------
@@ -173,16 +210,10 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a
 
     // ---------------- phase 3: coalesced tail ----------------
     const int lane = tid & 31, wid = tid >> 5;
-    const float* R0 = nullptr;
-    const float* R1 = nullptr;
-    if (a.Mout) {
-        R0 = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
-        R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
-    }
     if (a.flow || a.Mout) {
         float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
         float* Mo = a.Mout ? a.Mout + (size_t)p * a.m_stride : nullptr;
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < 16; ++i) {
             const int r = wid * 4 + (i >> 2), cx = (i & 3) * 32 + lane;
             const int x = x0 + cx, y = y0 + r;
@@ -191,7 +222,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a
                 if (fo) fo[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x] = f;
                 if (Mo) {
                     float mm[5];
-                    update_px(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
+                    update_px_any<RH>(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
                     store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, mm);
                 }
             }
@@ -242,13 +273,18 @@ inline bool blur_solve_fast_aligned(const BlurSolveArgs& a) {
     return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0 && blur_solve_fast_shape(a.w);
 }
 
-inline void launch_blur_solve_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
+template <bool RH>
+inline void launch_blur_solve_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
     using C = FastBoxCfg<7>;
     // per device/context attribute; cheap enough to set on every launch (one process may own several plans)
-    cudaFuncSetAttribute(k_blur_solve_box<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaFuncSetAttribute(k_blur_solve_box<7, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     const float reg = 1e-3f / (wc.scale * wc.scale);
     dim3 g((a.w + kFbTW - 1) / kFbTW, (a.h + kFbTH - 1) / kFbTH, np);
-    k_blur_solve_box<7><<<g, 256, C::SMEM, st>>>(a, reg);
+    k_blur_solve_box<7, RH><<<g, 256, C::SMEM, st>>>(a, reg);
+}
+inline void launch_blur_solve_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st) {
+    if (r_half) launch_blur_solve_fast_t<true>(a, wc, np, st);
+    else launch_blur_solve_fast_t<false>(a, wc, np, st);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -267,9 +303,9 @@ struct FastPeCfg {
     static constexpr size_t SMEM = (size_t)3 * kFbTH * VP * sizeof(float);
 };
 
-template <int N>
+template <int N, bool RH>
 __global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I, int pitch, size_t frame_stride, int w,
-                                                    int h, float* __restrict__ R, size_t plane_stride,
+                                                    int h, void* __restrict__ Rv, size_t plane_stride,
                                                     size_t slot_stride, int slot0, int nslots, const PolyCoef pc) {
     using C = FastPeCfg<N>;
     extern __shared__ __align__(16) float smem[];
@@ -303,7 +339,9 @@ __global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I,
     }
     __syncthreads();
     const int g = tid & 31, rb = tid >> 5;
-    float* Rb = R + (size_t)((slot0 + f) % nslots) * slot_stride;
+    const int slot = (slot0 + f) % nslots;
+    float* Rb = RH ? nullptr : static_cast<float*>(Rv) + (size_t)slot * slot_stride;
+    uint4* Rh = RH ? static_cast<uint4*>(Rv) + (size_t)slot * slot_stride : nullptr;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         const int r = rb + 8 * k;
@@ -343,7 +381,14 @@ __global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I,
             o[3][j] = fmaf(b1, pc.ig03, b4 * pc.ig33);
             o[4][j] = b6 * pc.ig55;
         }
-        if (y < h && x < w) {
+        if (RH) {
+            if (y < h) {
+                uint4* op = Rh + (size_t)y * pitch + x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x + j < w) op[j] = pack_r(o[0][j], o[1][j], o[2][j], o[3][j], o[4][j]);
+            }
+        } else if (y < h && x < w) {
             float* op = Rb + (size_t)y * pitch + x;
             if (x + 3 < w) {
 #pragma unroll
@@ -362,25 +407,30 @@ __global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I,
 
 inline bool polyexp_fast_supported(int n, int pitch) { return (n == 5 || n == 7) && (pitch % 4) == 0; }
 
-inline bool polyexp_fast_aligned(const float* R, size_t plane_stride, size_t slot_stride) {
+inline bool polyexp_fast_aligned(const void* R, size_t plane_stride, size_t slot_stride) {
     return aligned16(R) && (plane_stride % 4) == 0 && (slot_stride % 4) == 0;
 }
 
-template <int N>
-inline void launch_polyexp_fast_n(const float* I, int pitch, size_t frame_stride, int w, int h, float* R,
+template <int N, bool RH>
+inline void launch_polyexp_fast_n(const float* I, int pitch, size_t frame_stride, int w, int h, void* R,
                                   size_t plane_stride, size_t slot_stride, int slot0, int nslots, int nf,
                                   const PolyCoef& pc, cudaStream_t st) {
     using C = FastPeCfg<N>;
-    cudaFuncSetAttribute(k_polyexp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaFuncSetAttribute(k_polyexp<N, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     dim3 g((w + kFbTW - 1) / kFbTW, (h + kFbTH - 1) / kFbTH, nf);
-    k_polyexp<N><<<g, 256, C::SMEM, st>>>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, pc);
+    k_polyexp<N, RH><<<g, 256, C::SMEM, st>>>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, pc);
 }
 
-inline void launch_polyexp_fast(const float* I, int pitch, size_t frame_stride, int w, int h, float* R,
+inline void launch_polyexp_fast(const float* I, int pitch, size_t frame_stride, int w, int h, void* R,
                                 size_t plane_stride, size_t slot_stride, int slot0, int nslots, int nf,
-                                const PolyCoef& pc, cudaStream_t st) {
-    if (pc.n == 5) launch_polyexp_fast_n<5>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
-    else launch_polyexp_fast_n<7>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
+                                const PolyCoef& pc, bool r_half, cudaStream_t st) {
+    if (pc.n == 5) {
+        if (r_half) launch_polyexp_fast_n<5, true>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
+        else launch_polyexp_fast_n<5, false>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
+    } else {
+        if (r_half) launch_polyexp_fast_n<7, true>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
+        else launch_polyexp_fast_n<7, false>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, st);
+    }
 }
 
 }  // namespace bf

@@ -9,6 +9,7 @@
 //   flow             [pair][h][pitch] float2 (dx, dy)                                  bilinear gather coalesce
 // `pitch` is in elements and a multiple of 32 for plan-owned buffers (128-byte rows).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -209,25 +210,26 @@ __device__ __forceinline__ float border_w(int i, int n) {
 __device__ __forceinline__ void update_px(const float* __restrict__ R0, const float* __restrict__ R1,
                                           unsigned plane, unsigned pitch, int w, int h, int x, int y,
                                           float dx, float dy, float out[5]) {
-    const unsigned o = (unsigned)y * pitch + (unsigned)x;
     float q[5];
+    {
+        const float* pq = R0 + ((unsigned)y * pitch + (unsigned)x);
 #pragma unroll
-    for (int c = 0; c < 5; ++c) q[c] = __ldg(R0 + (size_t)c * plane + o);
+        for (int c = 0; c < 5; ++c) { q[c] = __ldg(pq); pq += plane; }
+    }
     float fx = (float)x + dx, fy = (float)y + dy;
     const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
     fx -= (float)x1;
     fy -= (float)y1;
     float r2, r3, r4, r5, r6;
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-        const unsigned o1 = (unsigned)y1 * pitch + (unsigned)x1;
-        const unsigned o2 = o1 + pitch;
+        const float* pa = R1 + ((unsigned)y1 * pitch + (unsigned)x1);
         float t0[5], t1[5], b0[5], b1[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-            const float* pa = R1 + (size_t)c * plane + o1;
-            const float* pb = R1 + (size_t)c * plane + o2;
+            const float* pb = pa + pitch;
             t0[c] = __ldg(pa); t1[c] = __ldg(pa + 1);
             b0[c] = __ldg(pb); b1[c] = __ldg(pb + 1);
+            pa += plane;
         }
         const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
         float rw[5];
@@ -260,8 +262,96 @@ __device__ __forceinline__ void update_px(const float* __restrict__ R0, const fl
 }
 
 __device__ __forceinline__ void store_m(float* __restrict__ M, unsigned plane, unsigned o, const float m[5]) {
+    float* pm = M + o;
 #pragma unroll
-    for (int c = 0; c < 5; ++c) M[(size_t)c * plane + o] = m[c];
+    for (int c = 0; c < 5; ++c) { *pm = m[c]; pm += plane; }
+}
+
+// ---- packed polynomial coefficients: 8 x fp16 per pixel (5 used), one 128-bit load per bilinear tap --------------
+// Storage format only: all arithmetic stays fp32.  fp16 storage of R costs <= 5e-4 px max / 6e-5 px mean endpoint error
+// against cv2 (tests/test_gpu_flow.py), 100x inside the parity gate, and turns the 20 scalar gather
+// loads + 5 centre loads per pixel into 4 + 1 LDG.128.  Used for uint8 input only (|R| is bounded by the 0..255 range).
+struct __align__(16) RPix { __half2 a, b, c, d; };   // (b_y, b_x), (A_yy, A_xx), (A_xy, 0), (0, 0)
+
+__device__ __forceinline__ uint4 pack_r(float r0, float r1, float r2, float r3, float r4) {
+    union { uint4 u; __half2 h[4]; } t;
+    t.h[0] = __floats2half2_rn(r0, r1);
+    t.h[1] = __floats2half2_rn(r2, r3);
+    t.h[2] = __floats2half2_rn(r4, 0.f);
+    t.h[3] = __floats2half2_rn(0.f, 0.f);
+    return t.u;
+}
+
+__device__ __forceinline__ void unpack_r(const uint4& u, float v[5]) {
+    union { uint4 u; __half2 h[4]; } t;
+    t.u = u;
+    const float2 a = __half22float2(t.h[0]), b = __half22float2(t.h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = __low2float(t.h[2]);
+}
+
+// UpdateMatrices for one pixel from packed R (same arithmetic as update_px).  R0/R1 point at pixel (0,0) of the frame.
+__device__ __forceinline__ void update_px_h(const uint4* __restrict__ R0, const uint4* __restrict__ R1, unsigned pitch,
+                                            int w, int h, int x, int y, float dx, float dy, float out[5]) {
+    float q[5];
+    unpack_r(__ldg(R0 + (unsigned)y * pitch + (unsigned)x), q);
+    float fx = (float)x + dx, fy = (float)y + dy;
+    const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+    fx -= (float)x1;
+    fy -= (float)y1;
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const uint4* pa = R1 + (unsigned)y1 * pitch + (unsigned)x1;
+        const uint4 u00 = __ldg(pa), u01 = __ldg(pa + 1), u10 = __ldg(pa + pitch), u11 = __ldg(pa + pitch + 1);
+        float t00[5], t01[5], t10[5], t11[5];
+        unpack_r(u00, t00); unpack_r(u01, t01); unpack_r(u10, t10); unpack_r(u11, t11);
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        float rw[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) rw[c] = a00 * t00[c] + a01 * t01[c] + a10 * t10[c] + a11 * t11[c];
+        r2 = rw[0];
+        r3 = rw[1];
+        r4 = (q[2] + rw[2]) * 0.5f;
+        r5 = (q[3] + rw[3]) * 0.5f;
+        r6 = (q[4] + rw[4]) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = q[2];
+        r5 = q[3];
+        r6 = q[4] * 0.5f;
+    }
+    r2 = (q[0] - r2) * 0.5f;
+    r3 = (q[1] - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float sc = border_w(x, w) * border_w(y, h);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    out[0] = r4 * r4 + r6 * r6;
+    out[1] = (r4 + r5) * r6;
+    out[2] = r5 * r5 + r6 * r6;
+    out[3] = r4 * r2 + r6 * r3;
+    out[4] = r6 * r2 + r5 * r3;
+}
+
+// R0/R1 of pair p in the frame ring (p < nslots, slot0 < nslots: one conditional subtract instead of an integer modulo).
+__device__ __forceinline__ int ring_slot(int slot0, int p, int nslots) {
+    const int s = slot0 + p;
+    return s >= nslots ? s - nslots : s;
+}
+
+// Layout-agnostic front end: RH = packed fp16 (slot_stride counts uint4 pixels), else fp32 planes (slot_stride in floats).
+template <bool RH>
+__device__ __forceinline__ void update_px_any(const void* R0, const void* R1, unsigned plane, unsigned pitch, int w, int h,
+                                              int x, int y, float dx, float dy, float out[5]) {
+    if (RH) update_px_h(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), pitch, w, h, x, y, dx, dy, out);
+    else update_px(static_cast<const float*>(R0), static_cast<const float*>(R1), plane, pitch, w, h, x, y, dx, dy, out);
+}
+
+template <bool RH>
+__device__ __forceinline__ const void* r_slot_ptr(const void* R, size_t slot_stride, int slot) {
+    if (RH) return static_cast<const uint4*>(R) + (size_t)slot * slot_stride;
+    return static_cast<const float*>(R) + (size_t)slot * slot_stride;
 }
 
 struct ResizeTab {
@@ -275,8 +365,9 @@ __device__ __forceinline__ float2 upsample_flow_px(const float2* __restrict__ fc
     const int x0 = t.ix[x], y0 = t.iy[y];
     const float a = t.ax[x], b = t.ay[y];
     const int x1 = min(x0 + 1, ws - 1), y1 = min(y0 + 1, hs - 1);
-    const float2 p00 = fc[(size_t)y0 * pitch_c + x0], p01 = fc[(size_t)y0 * pitch_c + x1];
-    const float2 p10 = fc[(size_t)y1 * pitch_c + x0], p11 = fc[(size_t)y1 * pitch_c + x1];
+    const unsigned r0 = (unsigned)y0 * (unsigned)pitch_c, r1 = (unsigned)y1 * (unsigned)pitch_c;
+    const float2 p00 = fc[r0 + (unsigned)x0], p01 = fc[r0 + (unsigned)x1];
+    const float2 p10 = fc[r1 + (unsigned)x0], p11 = fc[r1 + (unsigned)x1];
     const float h0x = p00.x * (1.f - a) + p01.x * a, h0y = p00.y * (1.f - a) + p01.y * a;
     const float h1x = p10.x * (1.f - a) + p11.x * a, h1y = p10.y * (1.f - a) + p11.y * a;
     float2 r;
@@ -287,7 +378,7 @@ __device__ __forceinline__ float2 upsample_flow_px(const float2* __restrict__ fc
 
 // K3a: M = UpdateMatrices(R0, R1, flow_init).  flow_mode: 0 = zero, 1 = flow buffer, 2 = upsample coarse.
 struct UpdateArgs {
-    const float* R; size_t plane_stride, slot_stride; int slot0, nslots;  // R0 = slot (slot0+p), R1 = next
+    const void* R; size_t plane_stride, slot_stride; int slot0, nslots;   // R0 = ring slot (slot0+p), R1 = the next one
     int pitch, w, h;
     int flow_mode;
     const float2* flow; int flow_pitch; size_t flow_stride;              // mode 1: [pair][h][flow_pitch]; mode 2: coarse
@@ -296,21 +387,22 @@ struct UpdateArgs {
     float2* flow_out; int flow_out_pitch; size_t flow_out_stride;          // optional: write flow_init
 };
 
+template <bool RH>
 __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int p = blockIdx.z;
     if (x >= a.w || y >= a.h) return;
     float2 fl = make_float2(0.f, 0.f);
-    if (a.flow_mode == 1) fl = a.flow[(size_t)p * a.flow_stride + (size_t)y * a.flow_pitch + x];
+    if (a.flow_mode == 1) fl = a.flow[(size_t)p * a.flow_stride + (unsigned)y * (unsigned)a.flow_pitch + (unsigned)x];
     else if (a.flow_mode == 2)
         fl = upsample_flow_px(a.flow + (size_t)p * a.flow_stride, a.flow_pitch, a.ws, a.hs, a.tab, x, y, a.mult);
-    if (a.flow_out) a.flow_out[(size_t)p * a.flow_out_stride + (size_t)y * a.flow_out_pitch + x] = fl;
+    if (a.flow_out) a.flow_out[(size_t)p * a.flow_out_stride + (unsigned)y * (unsigned)a.flow_out_pitch + (unsigned)x] = fl;
     if (!a.M) return;
-    const float* R0 = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
-    const float* R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
+    const void* R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
+    const void* R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
     float m[5];
-    update_px(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, a.w, a.h, x, y, fl.x, fl.y, m);
+    update_px_any<RH>(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, a.w, a.h, x, y, fl.x, fl.y, m);
     store_m(a.M + (size_t)p * a.m_stride, (unsigned)a.plane_stride, (unsigned)y * (unsigned)a.pitch + (unsigned)x, m);
 }
 
@@ -328,7 +420,7 @@ struct BlurSolveArgs {
     // outputs (each optional)
     float2* flow; int flow_pitch; size_t flow_stride;
     float* Mout;
-    const float* R; size_t slot_stride; int slot0, nslots;  // for Mout
+    const void* R; size_t slot_stride; int slot0, nslots;   // for Mout (fp32 planes, or packed fp16 pixels)
     // ROI reduction (optional): masks [n_roi][h][w] u8; axes per pair; partial [pair][roi][ncta][4]
     const uint8_t* masks; int n_roi; size_t mask_stride; int mask_pitch;
     const float* axes;  // [pair][4] = ex0, ex1, ey0, ey1
@@ -387,6 +479,7 @@ __device__ __forceinline__ void roi_reduce_store(const BlurSolveArgs& a, int p, 
     }
 }
 
+template <bool RH>
 __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs a, const WinCoef wc) {
     __shared__ float V[5][kBsTH][kBsTW + 2 * kMaxWinHalf];
     __shared__ float s_red[8 * 4];
@@ -442,10 +535,10 @@ __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs 
     if (valid) {
         if (a.flow) a.flow[(size_t)p * a.flow_stride + (size_t)y * a.flow_pitch + x] = fl;
         if (a.Mout) {
-            const float* R0 = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
-            const float* R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
+            const void* R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
+            const void* R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
             float mm[5];
-            update_px(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, w, h, x, y, fl.x, fl.y, mm);
+            update_px_any<RH>(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, w, h, x, y, fl.x, fl.y, mm);
             store_m(a.Mout + (size_t)p * a.m_stride, (unsigned)a.plane_stride, (unsigned)y * (unsigned)a.pitch + (unsigned)x, mm);
         }
     }

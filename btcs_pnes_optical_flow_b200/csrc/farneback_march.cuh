@@ -56,7 +56,7 @@ struct MarchArgs {
     float reg;        // 1e-3 / scale^2
 };
 
-template <int MH>
+template <int MH, bool RH>
 __global__ void __launch_bounds__(MarchCfg<MH>::NT, 1) k_flow_iter_box(const MarchArgs ma) {
     using C = MarchCfg<MH>;
     extern __shared__ __align__(16) float smem[];
@@ -85,8 +85,16 @@ __global__ void __launch_bounds__(MarchCfg<MH>::NT, 1) k_flow_iter_box(const Mar
             const int r = min(max(row, 0), h - 1);
             return __ldg(reinterpret_cast<const float4*>(src + (unsigned)r * pitch));
         };
+        // Far-ahead L2 prefetch (no registers held): one lane per 128-byte line pulls rows kL2Ahead ahead of the register
+        // prefetch queue, so the LDG.128 stream below pays L2 latency, not HBM latency.
+        constexpr int kL2Ahead = 40;
+        const bool pf_lane = active && mode == 0 && ((q & 7) == 0);
+        auto pf_row = [&](int row) {
+            if (pf_lane && row < h) prefetch_l2(src + (unsigned)max(row, 0) * pitch);
+        };
         float4 win[C::WIN], pre[C::PF];
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < kL2Ahead; ++i) pf_row(ya + MH + 1 + C::PF + i);
         if (active) {
 #pragma unroll
             for (int i = 0; i < C::WIN; ++i) win[i] = ld(ya - MH + i);
@@ -108,6 +116,7 @@ __global__ void __launch_bounds__(MarchCfg<MH>::NT, 1) k_flow_iter_box(const Mar
                         const int slot = (j + C::WIN - 1) % C::WIN, ps = (j + C::PF - 1) % C::PF;
                         const float4 nv = pre[ps];
                         pre[ps] = ld(ybase + j + MH + C::PF);
+                        pf_row(ybase + j + MH + C::PF + kL2Ahead);
                         const float4 ov = win[slot];
                         win[slot] = nv;
                         if (j > 0) s = f4add(s, f4sub(nv, ov));
@@ -132,11 +141,11 @@ __global__ void __launch_bounds__(MarchCfg<MH>::NT, 1) k_flow_iter_box(const Mar
         // =========================== COMPUTE WARPS ===========================
         const int ctid = tid - C::NL;
         const int lane = ctid & 31, cw = ctid >> 5;
-        const float* R0 = nullptr;
-        const float* R1 = nullptr;
+        const void* R0 = nullptr;
+        const void* R1 = nullptr;
         if (a.Mout) {
-            R0 = a.R + (size_t)((a.slot0 + p) % a.nslots) * a.slot_stride;
-            R1 = a.R + (size_t)((a.slot0 + p + 1) % a.nslots) * a.slot_stride;
+            R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
+            R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
         }
         float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
         float* Mo = a.Mout ? a.Mout + (size_t)p * a.m_stride : nullptr;
@@ -151,6 +160,8 @@ __global__ void __launch_bounds__(MarchCfg<MH>::NT, 1) k_flow_iter_box(const Mar
         for (int blk = 0; blk < nblk; ++blk) {
             const int buf = blk & 1;
             const int ybase = ya + blk * C::RB;
+            // pull what this block's tail will gather into L2 while the horizontal pass runs
+            if (Mo) prefetch_r_block<RH>(R0, R1, plane, pitch, w, h, x0, ybase, C::RB, ctid, C::NCMP);
             named_bar_sync(buf ? BAR_FULL1 : BAR_FULL0, C::NT);
             // ---- horizontal sums + solve: GPT groups of 4 pixels per thread ----
             float2 fl[C::GPT][4];
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(MarchCfg<MH>::NT, 1) k_flow_iter_box(const Mar
                         if (fo) fo[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x] = f;
                         if (Mo) {
                             float mm[5];
-                            update_px(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
+                            update_px_any<RH>(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
                             store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, mm);
                         }
                     }
@@ -283,14 +294,20 @@ inline int march_ncta(int w, int h, int np, int sm_count) {
     return nstrip * nseg;
 }
 
-inline void launch_march(const BlurSolveArgs& a, const WinCoef& wc, int np, int sm_count, cudaStream_t st) {
+template <bool RH>
+inline void launch_march_t(const MarchArgs& ma, int np, cudaStream_t st) {
     using C = MarchCfg<7>;
+    cudaFuncSetAttribute(k_flow_iter_box<7, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    k_flow_iter_box<7, RH><<<np * ma.nstrip * ma.nseg, C::NT, C::SMEM, st>>>(ma);
+}
+
+inline void launch_march(const BlurSolveArgs& a, const WinCoef& wc, int np, int sm_count, bool r_half, cudaStream_t st) {
     MarchArgs ma;
     ma.a = a;
     march_plan(a.w, a.h, np, sm_count, ma.nstrip, ma.nseg, ma.seg_rows);
     ma.reg = 1e-3f / (wc.scale * wc.scale);
-    cudaFuncSetAttribute(k_flow_iter_box<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    k_flow_iter_box<7><<<np * ma.nstrip * ma.nseg, C::NT, C::SMEM, st>>>(ma);
+    if (r_half) launch_march_t<true>(ma, np, st);
+    else launch_march_t<false>(ma, np, st);
 }
 
 }  // namespace bf

@@ -67,7 +67,9 @@ class FlowPlan:
     """Owns the device workspace for W x H frames and one Farneback parameter set (bf_plan)."""
 
     def __init__(self, width: int, height: int, params: dict | None = None, max_pairs: int = 8,
-                 max_rois: int = 1, device: int | None = None):
+                 max_rois: int = 1, device: int | None = None, exact: bool = False):
+        """exact=True keeps the polynomial coefficients as float32 planes (needed for float32 input frames); the
+        default packs them as fp16 for poly_n 5/7 (storage only, <= 5e-4 px against cv2)."""
         self._lib = _lib.load()
         self.params = dict(FB_PARAMS, **(params or {}))
         self.width, self.height = int(width), int(height)
@@ -83,8 +85,9 @@ class FlowPlan:
         self.device = int(device)
         handle = C.c_void_p()
         ps = _params_struct(self.params)
-        check(self._lib.bf_plan_create(C.byref(ps), self.width, self.height, self.max_pairs, self.max_rois,
-                                       self.device, C.byref(handle)))
+        self.exact = bool(exact)
+        check(self._lib.bf_plan_create_ex(C.byref(ps), self.width, self.height, self.max_pairs, self.max_rois,
+                                          self.device, _lib.BF_PLAN_EXACT_F32 if exact else 0, C.byref(handle)))
         self._h = handle
 
     # -- lifecycle -----------------------------------------------------------------------------------
@@ -120,6 +123,10 @@ class FlowPlan:
                                                C.byref(pitch)))
             out.append(dict(w=w.value, h=h.value, ksize=k.value, sigma=s.value, pitch=pitch.value))
         return out
+
+    @property
+    def coeff_storage_bits(self) -> int:
+        return int(self._lib.bf_plan_coeff_storage(self._h))
 
     def level_pixels(self) -> int:
         return sum(s["w"] * s["h"] for s in self.scales())
@@ -310,13 +317,13 @@ _plans_lock = threading.Lock()
 
 
 def get_plan(width: int, height: int, params: dict | None = None, max_pairs: int = 1, max_rois: int = 1,
-             device: int | None = None) -> FlowPlan:
+             device: int | None = None, exact: bool = False) -> FlowPlan:
     p = dict(FB_PARAMS, **(params or {}))
-    key = (width, height, max_pairs, max_rois, device, tuple(sorted(p.items())))
+    key = (width, height, max_pairs, max_rois, device, exact, tuple(sorted(p.items())))
     with _plans_lock:
         plan = _plans.get(key)
         if plan is None:
-            plan = _plans[key] = FlowPlan(width, height, p, max_pairs, max_rois, device)
+            plan = _plans[key] = FlowPlan(width, height, p, max_pairs, max_rois, device, exact)
         return plan
 
 
@@ -336,17 +343,20 @@ def calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, itera
     if not float(pyr_scale) < 1.0:
         raise Cv2CompatError(-1, _CV2_ASSERT)
     if _is_torch(prev):
+        import torch
         H, W = int(prev.shape[0]), int(prev.shape[1])
         if prev.dim() != 2 or tuple(prev.shape) != tuple(next.shape):
             raise Cv2CompatError(-1, _CV2_ASSERT)
         device = prev.device.index
+        exact = not (prev.dtype == torch.uint8 and next.dtype == torch.uint8)
     else:
-        prev, next, _ = _coerce_pair(prev, next)
+        prev, next, dt = _coerce_pair(prev, next)
         H, W = prev.shape
         device = None
+        exact = dt != BF_DTYPE_U8
     params = dict(pyr_scale=pyr_scale, levels=levels, winsize=winsize, iterations=iterations, poly_n=poly_n,
                   poly_sigma=poly_sigma, flags=flags)
-    return get_plan(W, H, params, max_pairs=1, max_rois=1, device=device).flow_pair(prev, next, flow)
+    return get_plan(W, H, params, max_pairs=1, max_rois=1, device=device, exact=exact).flow_pair(prev, next, flow)
 
 
 def build_roi_mask(H: int, W: int, roi_polygon_xy: np.ndarray) -> np.ndarray:

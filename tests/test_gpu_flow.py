@@ -76,7 +76,10 @@ def test_known_answers_and_input_conventions():
     f_u8 = B.calcOpticalFlowFarneback(a, b, None, **p)
     f_f32 = B.calcOpticalFlowFarneback(a.astype(np.float32), b.astype(np.float32), None, **p)
     f_f64 = B.calcOpticalFlowFarneback(a.astype(np.float64), b.astype(np.float64), None, **p)
-    assert np.array_equal(f_u8, f_f32) and np.array_equal(f_u8, f_f64)            # f32 0..255 == u8 bit for bit
+    assert np.array_equal(f_f32, f_f64)                                           # non-u8 input -> float32, exact plan
+    with B.FlowPlan(160, 120, p, exact=True) as ex:                               # f32 0..255 == u8 bit for bit (cv2 too)
+        assert ex.coeff_storage_bits == 32 and np.array_equal(ex.flow_pair(a, b), f_f32)
+    assert epe(f_u8, f_f32)[1] < MAX_TIGHT                                        # packed-fp16 coefficient storage
     small = B.calcOpticalFlowFarneback(a[:20, :20], b[:20, :20], None, **p)        # < 32 px -> single scale
     assert epe(small, cv2_ref.farneback(np.ascontiguousarray(a[:20, :20]), np.ascontiguousarray(b[:20, :20]), **p))[1] < MAX_TIGHT
     view_a, view_b = a[::2, ::2], b[::2, ::2]                                     # non-contiguous views accepted
@@ -98,9 +101,9 @@ def test_torch_tensors_stay_on_device():
 
 
 def test_all_kernel_variants_agree(monkeypatch):
-    """The same parameters through the three implementations of the iteration kernel -- warp-specialised
-    strip-marching (default), tile (BTCSFLOW_KERNEL=tile), runtime-parameter (BTCSFLOW_NO_FAST=1) -- all inside the
-    tight gate against cv2 and within float rounding of each other."""
+    """The same parameters through the three implementations of the iteration kernel -- tile (default), warp-specialised
+    strip-marching (BTCSFLOW_KERNEL=march), runtime-parameter (BTCSFLOW_NO_FAST=1) -- and both coefficient storage
+    formats, all inside the tight gate against cv2 and within float rounding of each other."""
     import btcs_pnes_optical_flow_b200 as B
     from oracle import cv2_ref
     for (h, w) in ((270, 480), (203, 316)):
@@ -108,7 +111,10 @@ def test_all_kernel_variants_agree(monkeypatch):
         for p in (B.FB_PARAMS, dict(B.FB_PARAMS, levels=5, winsize=21, poly_n=7, poly_sigma=1.5, flags=256)):
             ref = cv2_ref.farneback(a, b, **p)
             outs = {}
-            for name, env in (("march", {}), ("tile", {"BTCSFLOW_KERNEL": "tile"}), ("generic", {"BTCSFLOW_NO_FAST": "1"})):
+            for name, env in (("tile", {}), ("march", {"BTCSFLOW_KERNEL": "march"}),
+                              ("tile_f32", {"BTCSFLOW_R_STORAGE": "f32"}),
+                              ("march_f32", {"BTCSFLOW_KERNEL": "march", "BTCSFLOW_R_STORAGE": "f32"}),
+                              ("generic", {"BTCSFLOW_NO_FAST": "1"})):
                 for k, v in env.items():
                     monkeypatch.setenv(k, v)
                 with B.FlowPlan(w, h, p) as plan:
@@ -117,7 +123,8 @@ def test_all_kernel_variants_agree(monkeypatch):
                     monkeypatch.delenv(k)
                 mean, mx = epe(outs[name], ref)
                 assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (name, h, w, mean, mx)
-            assert epe(outs["march"], outs["generic"])[1] < 1e-3 and epe(outs["tile"], outs["generic"])[1] < 1e-3
+            assert epe(outs["march_f32"], outs["generic"])[1] < 1e-4 and epe(outs["tile_f32"], outs["generic"])[1] < 1e-4
+            assert epe(outs["march"], outs["generic"])[1] < 2e-3 and epe(outs["tile"], outs["march"])[1] < 1e-4
 
 
 def test_1080p_full_size_properties():

