@@ -181,6 +181,7 @@ struct ScaleInfo {
     int *fix = nullptr, *fiy = nullptr;     // flow upsample: next-coarser scale -> this scale
     float *fax = nullptr, *fay = nullptr;
     float* I = nullptr;                       // [F][h][pitch]
+    float* tmpk = nullptr;                    // horizontal-pass scratch of this level [F][H][pitch] (levels coarser than 0)
     void* R = nullptr;                        // fp32 planes [F][5][h][pitch], or packed fp16 pixels [F][h][pitch] x 16 B
     float2* flow = nullptr;                   // [B][h][pitch]
 };
@@ -352,11 +353,42 @@ int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np,
 template <typename T>
 int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_bytes, int tf, int nf,
                   cudaStream_t st) {
+    if (p->use_fast && p->W * (int)sizeof(float) <= 160 * 1024) {
+        // level 0: exact 3x3 stencil; coarser levels: one multi-level horizontal pass + per-level vertical pass
+        bf::PyrHArgs pa{};
+        for (auto& s : p->sc) {
+            if (s.k == 0) {
+                dim3 g(cdiv(p->W, bf::kL0TW), cdiv(p->H, bf::kL0TH), nf);
+                bf::k_level0_blur<T><<<g, 256, 0, st>>>(frames, pitch_bytes, frame_bytes, p->W, p->H, s.I, s.pitch, s.plane);
+                LAUNCH_CHECK();
+            } else if (pa.nlev < bf::kPyrMaxLevels) {
+                bf::PyrLevelDesc& d = pa.lv[pa.nlev++];
+                d.ix = s.ix; d.ax = s.ax; d.kern = s.kern; d.ksize = s.ksize; d.w = s.w;
+                d.tmp = s.tmpk; d.tmp_pitch = s.pitch; d.tmp_frame_stride = (size_t)p->H * s.pitch;
+            }
+        }
+        if (pa.nlev > 0) {
+            const size_t smem = (size_t)p->W * sizeof(float);
+            cudaFuncSetAttribute(bf::k_pyr_h_multi<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            bf::k_pyr_h_multi<T><<<dim3(p->H, nf), 256, smem, st>>>(frames, pitch_bytes, frame_bytes, p->W, pa);
+            LAUNCH_CHECK();
+            for (auto& s : p->sc) {
+                if (s.k == 0) continue;
+                dim3 b(64, 4), g2(cdiv(s.w, 64), cdiv(s.h, 4), nf);
+                bf::k_pyr_v<<<g2, b, 0, st>>>(s.tmpk, s.pitch, (size_t)p->H * s.pitch, p->H, s.w, s.h, s.iy, s.ay, s.kern,
+                                              s.ksize, s.I, s.pitch, s.plane);
+                LAUNCH_CHECK();
+            }
+        }
+    } else {
+        for (auto& s : p->sc) {
+            int rc = launch_pyramid<T>(p, s, frames, pitch_bytes, frame_bytes, nf, s.I, s.pitch, s.plane, st);
+            if (rc) return rc;
+        }
+    }
     for (auto& s : p->sc) {
-        int rc = launch_pyramid<T>(p, s, frames, pitch_bytes, frame_bytes, nf, s.I, s.pitch, s.plane, st);
-        if (rc) return rc;
-        rc = launch_polyexp(s.I, s.pitch, s.plane, s.w, s.h, s.R, s.plane, p->r_half ? s.plane : 5 * s.plane, tf % p->F,
-                            p->F, nf, p->pc, p->use_fast, p->r_half, st);
+        int rc = launch_polyexp(s.I, s.pitch, s.plane, s.w, s.h, s.R, s.plane, p->r_half ? s.plane : 5 * s.plane, tf % p->F,
+                                p->F, nf, p->pc, p->use_fast, p->r_half, st);
         if (rc) return rc;
     }
     return 0;
@@ -575,6 +607,7 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
             if (upload(idx, &s.fiy) != cudaSuccess || upload(wgt, &s.fay) != cudaSuccess) return cleanup_fail(fail(2, "table upload failed"));
         }
         if ((rc = plan_alloc(p, &s.I, (size_t)p->F * s.plane))) return cleanup_fail(rc);
+        if (s.k > 0 && (rc = plan_alloc(p, &s.tmpk, (size_t)p->F * height * s.pitch))) return cleanup_fail(rc);
         {
             uint8_t* rbuf = nullptr;
             const size_t rbytes = (size_t)p->F * s.plane * (p->r_half ? sizeof(uint4) : 5 * sizeof(float));
@@ -613,7 +646,7 @@ int bf_plan_destroy(bf_plan* p) {
     for (auto& s : p->sc) {
         cudaFree(s.ix); cudaFree(s.iy); cudaFree(s.ax); cudaFree(s.ay); cudaFree(s.kern);
         cudaFree(s.fix); cudaFree(s.fiy); cudaFree(s.fax); cudaFree(s.fay);
-        cudaFree(s.I); cudaFree(s.R); cudaFree(s.flow);
+        cudaFree(s.I); cudaFree(s.R); cudaFree(s.flow); cudaFree(s.tmpk);
     }
     cudaFree(p->tmp); cudaFree(p->M[0]); cudaFree(p->M[1]); cudaFree(p->axes); cudaFree(p->partial);
     cudaFree(p->stage[0]); cudaFree(p->stage[1]); cudaFree(p->stage_flow);

@@ -405,6 +405,95 @@ __global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Pyramid.  Every level is made from the FULL-RESOLUTION frame: GaussianBlur(REFLECT_101) then bilinear
+// resize.  Scale 1.0 (level k = 0) always uses the fixed [1 2 1]/4 taps and no resize: k_level0_blur does that 3x3
+// stencil from a shared uint8->float tile (for uint8 input every product and partial sum is exactly representable, so
+// the result is bit-identical to cv2's row-then-column order).  Coarser levels: k_pyr_h_multi evaluates the horizontal
+// blur only at the columns the resize samples, for ALL coarser levels from one shared copy of each source row.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kL0TW = 128, kL0TH = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_level0_blur(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes,
+                                                     int W, int H, float* __restrict__ out, int out_pitch,
+                                                     size_t out_frame_stride) {
+    __shared__ float t[kL0TH + 2][kL0TW + 4];
+    const int x0 = blockIdx.x * kL0TW, y0 = blockIdx.y * kL0TH, f = blockIdx.z;
+    const char* base = (const char*)src + (size_t)f * src_frame_bytes;
+    for (int e = threadIdx.x; e < (kL0TH + 2) * (kL0TW + 2); e += 256) {
+        const int ry = e / (kL0TW + 2), rx = e - ry * (kL0TW + 2);
+        const int gy = reflect101(min(y0 + ry - 1, H), H), gx = reflect101(min(x0 + rx - 1, W), W);
+        t[ry][rx] = load_px((const T*)(base + (size_t)gy * src_pitch_bytes) + gx);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, rb = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = rb + 8 * k, y = y0 + r;
+        if (y >= H) continue;
+        float* orow = out + (size_t)f * out_frame_stride + (size_t)y * out_pitch;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cx = lane + 32 * j, x = x0 + cx;                       // lanes on consecutive pixels: no bank conflicts
+            float hr[3];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const float* q = &t[r + dy][cx];
+                hr[dy] = q[0] * 0.25f + q[1] * 0.5f + q[2] * 0.25f;          // row filter first, like cv2
+            }
+            if (x < W) orow[x] = hr[0] * 0.25f + hr[1] * 0.5f + hr[2] * 0.25f;
+        }
+    }
+}
+
+struct PyrLevelDesc {
+    const int* ix; const float* ax; const float* kern;
+    float* tmp; size_t tmp_frame_stride;
+    int ksize, w, tmp_pitch;
+};
+constexpr int kPyrMaxLevels = 15;
+struct PyrHArgs { PyrLevelDesc lv[kPyrMaxLevels]; int nlev; };
+
+// One CTA per (source row, frame): the row is converted to float in shared memory once and every coarser level takes
+// its horizontally blurred + column-interpolated samples from it.
+template <typename T>
+__global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes,
+                                                     int W, const PyrHArgs pa) {
+    extern __shared__ float srow[];                                          // [W]
+    const int r = blockIdx.x, f = blockIdx.y;
+    const T* row = (const T*)((const char*)src + (size_t)f * src_frame_bytes + (size_t)r * src_pitch_bytes);
+    for (int x = threadIdx.x; x < W; x += 256) srow[x] = load_px(row + x);
+    __syncthreads();
+    for (int l = 0; l < pa.nlev; ++l) {
+        const PyrLevelDesc& d = pa.lv[l];
+        const int rad = d.ksize >> 1;
+        float* trow = d.tmp + (size_t)f * d.tmp_frame_stride + (size_t)r * d.tmp_pitch;
+        for (int x = threadIdx.x; x < d.w; x += 256) {
+            const int i0 = d.ix[x];
+            const float a = d.ax[x];
+            float b0 = 0.f, b1 = 0.f;
+            if (i0 - rad >= 0 && i0 + 1 + rad < W) {
+                float prev = srow[i0 - rad];
+                for (int j = 0; j < d.ksize; ++j) {
+                    const float nxt = srow[i0 - rad + j + 1];
+                    const float kj = __ldg(d.kern + j);
+                    b0 = fmaf(kj, prev, b0);
+                    b1 = fmaf(kj, nxt, b1);
+                    prev = nxt;
+                }
+            } else {
+                for (int j = 0; j < d.ksize; ++j) b0 = fmaf(__ldg(d.kern + j), srow[reflect101(i0 - rad + j, W)], b0);
+                if (a != 0.f) {
+                    const int i1 = min(i0 + 1, W - 1);
+                    for (int j = 0; j < d.ksize; ++j) b1 = fmaf(__ldg(d.kern + j), srow[reflect101(i1 - rad + j, W)], b1);
+                }
+            }
+            trow[x] = (a != 0.f) ? (b0 * (1.f - a) + b1 * a) : b0;
+        }
+    }
+}
+
 inline bool polyexp_fast_supported(int n, int pitch) { return (n == 5 || n == 7) && (pitch % 4) == 0; }
 
 inline bool polyexp_fast_aligned(const void* R, size_t plane_stride, size_t slot_stride) {
