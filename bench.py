@@ -271,8 +271,8 @@ def run_ours(args, spec, params):
                     "launches": prof["launches"], "avg_launch_ms": prof["total_ms"] / prof["launches"],
                     "algorithmic_bytes_per_launch": prof["pair_iterations"] * bytes_per_pair_iter / prof["launches"],
                     "kernel_share_of_step": prof["total_ms"] / ms_total, "peak_source": peak_src,
-                    "pipeline_bytes_per_pair": bpp, "pipeline_achieved_GBs": value * bpp / 1e9,
-                    "pipeline_frac": value * bpp / 1e9 / peak}
+                    "pipeline_bytes_per_pair": bpp, "pipeline_achieved_GBs_per_gpu": value / world * bpp / 1e9,
+                    "pipeline_frac": value / world * bpp / 1e9 / peak}
         assert pc1 is not None and pc1.shape == (T_total,)
         both = np.isfinite(pc1) & np.isfinite(pc1_h)
         if T_total >= 120:                      # long enough for the 2 s PCA window: the series must be usable
