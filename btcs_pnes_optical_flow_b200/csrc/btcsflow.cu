@@ -202,7 +202,7 @@ struct bf_plan {
     bf::PolyCoef pc;
     bf::WinCoef wc;
     float* tmp = nullptr;       // [F][H][pitch0]
-    float* M[2] = {nullptr, nullptr};
+    void* M[2] = {nullptr, nullptr};   // matrices ping-pong: f32 planes, or fp16 planes on compact plans
     float* axes = nullptr;      // [B][4]
     float* partial = nullptr;   // [B][max_rois][ncta][4]
     int ncta_max = 0;
@@ -628,11 +628,14 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
     }
     if ((rc = plan_alloc(p, &p->tmp, tmp_elems))) return cleanup_fail(rc);
     for (int i = 0; i < 2; ++i) {
-        if ((rc = plan_alloc(p, &p->M[i], m_elems))) return cleanup_fail(rc);
-        cudaMemset(p->M[i], 0, m_elems * sizeof(float));
+        uint8_t* mbuf = nullptr;
+        const size_t mbytes = m_elems * (p->r_half ? sizeof(__half) : sizeof(float));
+        if ((rc = plan_alloc(p, &mbuf, mbytes))) return cleanup_fail(rc);
+        cudaMemset(mbuf, 0, mbytes);
+        p->M[i] = mbuf;
     }
     if ((rc = plan_alloc(p, &p->axes, (size_t)p->B * 4))) return cleanup_fail(rc);
-    p->ncta_max = std::max({cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), bf::blur_solve_fast_ncta(fine.w, fine.h),
+    p->ncta_max = std::max({cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), cdiv(fine.w, bf::kFbTW) * cdiv(fine.h, 16),
                             cdiv(fine.w, bf::kFbTW) * 16});
     if ((rc = plan_alloc(p, &p->partial, (size_t)p->B * std::max(max_rois, 1) * p->ncta_max * bf::kRoiVals))) return cleanup_fail(rc);
     if (cudaDeviceSynchronize() != cudaSuccess) return cleanup_fail(fail(2, "plan initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));

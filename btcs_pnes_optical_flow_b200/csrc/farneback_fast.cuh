@@ -13,13 +13,15 @@
 //   phase 3  flow is transposed through shared memory so that lanes own consecutive pixels again: coalesced R0
 //            loads, bilinear R1 gather, M' stores; ROI sums reduced per CTA (deterministic partials).
 #pragma once
+#include <cstdlib>
+
 #include "farneback_kernels.cuh"
 
 namespace bf {
 
 constexpr int kFbTW = 128, kFbTH = 32;
 
-template <int MH>
+template <int MH, int TH = kFbTH>
 struct FastBoxCfg {
     static constexpr int HALO = (MH + 3) / 4 * 4;
     static constexpr int D = HALO - MH;                        // unused leading columns in the halo
@@ -27,10 +29,14 @@ struct FastBoxCfg {
     static constexpr int VP = kFbTW + 2 * HALO + 4;            // shared row pitch (floats, multiple of 4)
     static constexpr int WIN = 2 * MH + 1;
     static constexpr int NCH = (D + 2 * MH + 3) / 4 + 1;       // float4 chunks a 4-output group reads
-    static constexpr int V_FLOATS = 5 * kFbTH * VP;
+    static constexpr int V_FLOATS = 5 * TH * VP;
+    static constexpr int RG = TH / 8;                          // row groups per thread in phases 2/3
+    static constexpr int PF = TH >= 32 ? 8 : 4;                // register prefetch depth in phase 1
+    static constexpr int CTAS = TH >= 32 ? 2 : (TH >= 24 ? 3 : 4);   // CTAs per SM the shared-memory footprint allows
     static constexpr size_t SMEM = (size_t)(V_FLOATS + 64) * sizeof(float);
     static_assert(MH >= 2 && MH <= 16, "half window out of range for the fast path");
-    static_assert((size_t)kFbTH * kFbTW * sizeof(float2) <= (size_t)V_FLOATS * sizeof(float), "F must fit in V");
+    static_assert(TH % 8 == 0, "tile height must be a multiple of 8");
+    static_assert((size_t)TH * kFbTW * sizeof(float2) <= (size_t)V_FLOATS * sizeof(float), "F must fit in V");
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -40,14 +46,14 @@ __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4
 // Vertical (2MH+1)-row box sums of one float4 column for kFbTH consecutive output rows; register ring window, software
 // prefetch 4 rows ahead.  ROWS_IN: the tile's rows (with halo) lie inside the image, `src` already points at the first
 // halo row.  Otherwise rows are clamped to [0, h-1] (replicate) starting from row `yb`.
-template <int MH, bool ROWS_IN>
-__device__ __forceinline__ void vertical_box_sums(const float* __restrict__ src, unsigned pitch, int yb, int h, int mode,
+template <int MH, bool ROWS_IN, int TH, int PF, typename MT>
+__device__ __forceinline__ void vertical_box_sums(const MT* __restrict__ src, unsigned pitch, int yb, int h, int mode,
                                                   float* __restrict__ dst, int vp) {
-    constexpr int WIN = 2 * MH + 1, PF = 4, NROW = kFbTH + 2 * MH;
+    constexpr int WIN = 2 * MH + 1, NROW = TH + 2 * MH;
     auto ld = [&](int i) -> float4 {
-        if (ROWS_IN) return __ldg(reinterpret_cast<const float4*>(src + (unsigned)i * pitch));
+        if (ROWS_IN) return m_load4(src + (unsigned)i * pitch);
         const int r = min(max(yb + i, 0), h - 1);
-        return __ldg(reinterpret_cast<const float4*>(src + (unsigned)r * pitch));
+        return m_load4(src + (unsigned)r * pitch);
     };
     auto st = [&](int j, const float4& s) {
         float4 o = s;
@@ -66,7 +72,7 @@ __device__ __forceinline__ void vertical_box_sums(const float* __restrict__ src,
 #pragma unroll
     for (int i = 0; i < PF; ++i) pre[i] = ld(WIN + i);
 #pragma unroll
-    for (int j = 1; j < kFbTH; ++j) {
+    for (int j = 1; j < TH; ++j) {
         const float4 nv = pre[(j - 1) % PF];
         if (j - 1 + PF + WIN < NROW) pre[(j - 1) % PF] = ld(WIN + j - 1 + PF);
         const float4 ov = win[(j - 1) % WIN];
@@ -110,29 +116,31 @@ __device__ __forceinline__ void prefetch_r_block(const void* R0v, const void* R1
     }
 }
 
-template <int MH, bool RH>
-__global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a, const float reg) {
-    using C = FastBoxCfg<MH>;
+template <int MH, bool RH, int TH>
+__global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg) {
+    using C = FastBoxCfg<MH, TH>;
     extern __shared__ __align__(16) float smem[];
     float* V = smem;                                   // [5][TH][VP]
     float2* F = reinterpret_cast<float2*>(smem);       // [TH][TW], aliases V after phase 2
     float* s_red = smem + C::V_FLOATS;                 // [8][4]
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kFbTH, p = blockIdx.z;
+    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * TH, p = blockIdx.z;
     const int w = a.w, h = a.h;
     const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
-    const float* Mp = a.M + (size_t)p * a.m_stride;
+    using MT = typename MStore<RH>::type;
+    const MT* Mp = static_cast<const MT*>(a.M) + (size_t)p * a.m_stride;
+    constexpr int kLine = 128 / (int)sizeof(MT);                          // elements per 128-byte line
 
     // A lone CTA of this kernel takes ~22 us (ncu, profiles/): its time is a chain of HBM round trips, not bandwidth.
     // So the whole M tile (with halo) is requested into L2 up front -- phase 1's register-window stream then pays L2
     // latency per step -- and likewise what phase 3 will read (R0 under the tile, R1 around it), which travels from
     // HBM while phases 1-2 run.
     {
-        const int xlo = max(x0 - C::HALO, 0) & ~31, xhi = min(x0 + kFbTW + C::HALO, w);
-        const int nline = (xhi - xlo + 31) / 32, nrow = kFbTH + 2 * MH;
+        const int xlo = max(x0 - C::HALO, 0) & ~(kLine - 1), xhi = min(x0 + kFbTW + C::HALO, w);
+        const int nline = (xhi - xlo + kLine - 1) / kLine, nrow = TH + 2 * MH;
         for (int e = tid; e < 5 * nrow * nline; e += 256) {
             const int c = e / (nrow * nline), rem = e - c * (nrow * nline);
-            const int yy = min(max(y0 - MH + rem / nline, 0), h - 1), xx = xlo + (rem % nline) * 32;
+            const int yy = min(max(y0 - MH + rem / nline, 0), h - 1), xx = xlo + (rem % nline) * kLine;
             prefetch_l2(Mp + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
         }
     }
@@ -141,36 +149,36 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a
     if (a.Mout) {
         R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
         R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
-        prefetch_r_block<RH>(R0, R1, plane, pitch, w, h, x0, y0, kFbTH, tid, 256);
+        prefetch_r_block<RH>(R0, R1, plane, pitch, w, h, x0, y0, TH, tid, 256);
     }
 
     // ---------------- phase 1: vertical sums ----------------
     // w % 4 == 0 and float4-aligned columns: a float4 column is entirely inside the image, entirely left of it or
     // entirely right of it.  Outside columns load the nearest inside chunk and splat its edge lane when the SUM is
     // stored (replicate border; splat commutes with the sum), so the load path is branch-free.
-    const bool rows_in = (y0 - MH >= 0) && (y0 + kFbTH + MH <= h);      // block-uniform: no row clamping needed
+    const bool rows_in = (y0 - MH >= 0) && (y0 + TH + MH <= h);      // block-uniform: no row clamping needed
     for (int task = tid; task < 5 * C::NC4; task += 256) {
         const int c = task / C::NC4, q = task - c * C::NC4;
         const int gx = x0 - C::HALO + 4 * q;
         const int mode = gx < 0 ? 1 : (gx >= w ? 2 : 0);
         const int cgx = mode == 1 ? 0 : (mode == 2 ? w - 4 : gx);
-        const float* src = Mp + (size_t)c * plane + (unsigned)cgx;
-        float* dst = V + (size_t)c * kFbTH * C::VP + 4 * q;
-        if (rows_in) vertical_box_sums<MH, true>(src + (unsigned)(y0 - MH) * pitch, pitch, 0, 0, mode, dst, C::VP);
-        else vertical_box_sums<MH, false>(src, pitch, y0 - MH, h, mode, dst, C::VP);
+        const MT* src = Mp + (size_t)c * plane + (unsigned)cgx;
+        float* dst = V + (size_t)c * TH * C::VP + 4 * q;
+        if (rows_in) vertical_box_sums<MH, true, TH, C::PF>(src + (unsigned)(y0 - MH) * pitch, pitch, 0, 0, mode, dst, C::VP);
+        else vertical_box_sums<MH, false, TH, C::PF>(src, pitch, y0 - MH, h, mode, dst, C::VP);
     }
     __syncthreads();
 
     // ---------------- phase 2: horizontal sums + solve ----------------
     const int g = tid & 31, rb = tid >> 5;
-    float2 fl[4][4];
+    float2 fl[C::RG][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C::RG; ++k) {
         const int r = rb + 8 * k;
         float gs[5][4];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-            const float4* vp = reinterpret_cast<const float4*>(V + ((size_t)c * kFbTH + r) * C::VP) + g;
+            const float4* vp = reinterpret_cast<const float4*>(V + ((size_t)c * TH + r) * C::VP) + g;
             float vv[4 * C::NCH];
 #pragma unroll
             for (int i = 0; i < C::NCH; ++i) {
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a
     }
     __syncthreads();                                    // all reads of V done before F overwrites it
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < C::RG; ++k) {
         float4* fp = reinterpret_cast<float4*>(F + (rb + 8 * k) * kFbTW + 4 * g);
         fp[0] = make_float4(fl[k][0].x, fl[k][0].y, fl[k][1].x, fl[k][1].y);
         fp[1] = make_float4(fl[k][2].x, fl[k][2].y, fl[k][3].x, fl[k][3].y);
@@ -212,10 +220,10 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a
     const int lane = tid & 31, wid = tid >> 5;
     if (a.flow || a.Mout) {
         float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
-        float* Mo = a.Mout ? a.Mout + (size_t)p * a.m_stride : nullptr;
+        MT* Mo = a.Mout ? static_cast<MT*>(a.Mout) + (size_t)p * a.m_stride : nullptr;
 #pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int r = wid * 4 + (i >> 2), cx = (i & 3) * 32 + lane;
+        for (int i = 0; i < 4 * C::RG; ++i) {
+            const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
             const int x = x0 + cx, y = y0 + r;
             if (x < w && y < h) {
                 const float2 f = F[r * kFbTW + cx];
@@ -236,8 +244,8 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_box(const BlurSolveArgs a
             const uint8_t* mk = a.masks + (size_t)roi * a.mask_stride;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int r = wid * 4 + (i >> 2), cx = (i & 3) * 32 + lane;
+            for (int i = 0; i < 4 * C::RG; ++i) {
+                const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
                 const int x = x0 + cx, y = y0 + r;
                 if (x < w && y < h && mk[(size_t)y * a.mask_pitch + x] != 0) {
                     const float2 f = F[r * kFbTW + cx];
@@ -267,20 +275,34 @@ inline bool blur_solve_fast_supported(const WinCoef& wc, int pitch) {
 }
 // + the image width must be a multiple of 4 (float4 columns are all-inside or all-outside) and at least one chunk
 inline bool blur_solve_fast_shape(int w) { return (w % 4) == 0 && w >= 4; }
-inline int blur_solve_fast_ncta(int w, int h) { return ((w + kFbTW - 1) / kFbTW) * ((h + kFbTH - 1) / kFbTH); }
-
 inline bool blur_solve_fast_aligned(const BlurSolveArgs& a) {
     return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0 && blur_solve_fast_shape(a.w);
 }
+// Tile height: 32 rows = 95 KB shared -> 2 CTAs/SM; 24 rows = 71 KB -> 3 CTAs/SM (default: the kernel is latency-bound,
+// more resident CTAs win over the extra vertical halo; measured in profiles/); 16 rows -> 4 CTAs/SM.
+inline int tile_th() {
+    const char* e = getenv("BTCSFLOW_TILE_TH");
+    const int v = e ? atoi(e) : 24;
+    return (v == 16 || v == 32) ? v : 24;
+}
+inline int blur_solve_fast_ncta(int w, int h) { const int th = tile_th(); return ((w + kFbTW - 1) / kFbTW) * ((h + th - 1) / th); }
 
+template <bool RH, int TH>
+inline void launch_blur_solve_fast_th(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
+    using C = FastBoxCfg<7, TH>;
+    // per device/context attribute; cheap enough to set on every launch (one process may own several plans)
+    cudaFuncSetAttribute(k_blur_solve_box<7, RH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    const float reg = 1e-3f / (wc.scale * wc.scale);
+    dim3 g((a.w + kFbTW - 1) / kFbTW, (a.h + TH - 1) / TH, np);
+    k_blur_solve_box<7, RH, TH><<<g, 256, C::SMEM, st>>>(a, reg);
+}
 template <bool RH>
 inline void launch_blur_solve_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
-    using C = FastBoxCfg<7>;
-    // per device/context attribute; cheap enough to set on every launch (one process may own several plans)
-    cudaFuncSetAttribute(k_blur_solve_box<7, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    const float reg = 1e-3f / (wc.scale * wc.scale);
-    dim3 g((a.w + kFbTW - 1) / kFbTW, (a.h + kFbTH - 1) / kFbTH, np);
-    k_blur_solve_box<7, RH><<<g, 256, C::SMEM, st>>>(a, reg);
+    switch (tile_th()) {
+        case 16: launch_blur_solve_fast_th<RH, 16>(a, wc, np, st); break;
+        case 32: launch_blur_solve_fast_th<RH, 32>(a, wc, np, st); break;
+        default: launch_blur_solve_fast_th<RH, 24>(a, wc, np, st);
+    }
 }
 inline void launch_blur_solve_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st) {
     if (r_half) launch_blur_solve_fast_t<true>(a, wc, np, st);

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace bf {
 
 constexpr int kMaxPolyN = 16;
@@ -261,10 +263,29 @@ __device__ __forceinline__ void update_px(const float* __restrict__ R0, const fl
     out[4] = r6 * r2 + r5 * r3;
 }
 
-__device__ __forceinline__ void store_m(float* __restrict__ M, unsigned plane, unsigned o, const float m[5]) {
-    float* pm = M + o;
+// Compact plans (RH) also keep the matrices M as fp16 planes: |M| <= ~1.3e3 for uint8 frames (max over the probe set,
+// DESIGN.md), far from fp16 overflow; values below fp16's subnormal range vanish against the 1e-3 regulariser.  Measured
+// cost with both R and M in fp16: <= 3e-4 px mean, 2.2e-3 px max at 10 px flows (gate: 0.01 / 0.05).  Sums stay fp32.
+template <bool RH> struct MStore { using type = typename std::conditional<RH, __half, float>::type; };
+
+__device__ __forceinline__ float m_to_float(float v) { return v; }
+__device__ __forceinline__ float m_to_float(__half v) { return __half2float(v); }
+__device__ __forceinline__ void m_from_float(float* p, float v) { *p = v; }
+__device__ __forceinline__ void m_from_float(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ float4 m_load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 m_load4(const __half* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    union { unsigned v; __half2 h; } a, b;
+    a.v = u.x; b.v = u.y;
+    const float2 lo = __half22float2(a.h), hi = __half22float2(b.h);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <typename MT>
+__device__ __forceinline__ void store_m(MT* __restrict__ M, unsigned plane, unsigned o, const float m[5]) {
+    MT* pm = M + o;
 #pragma unroll
-    for (int c = 0; c < 5; ++c) { *pm = m[c]; pm += plane; }
+    for (int c = 0; c < 5; ++c) { m_from_float(pm, m[c]); pm += plane; }
 }
 
 // ---- packed polynomial coefficients: 8 x fp16 per pixel (5 used), one 128-bit load per bilinear tap --------------
@@ -383,7 +404,7 @@ struct UpdateArgs {
     int flow_mode;
     const float2* flow; int flow_pitch; size_t flow_stride;              // mode 1: [pair][h][flow_pitch]; mode 2: coarse
     int ws, hs; float mult; ResizeTab tab;
-    float* M; size_t m_stride;                                             // [pair][5][h][pitch]
+    void* M; size_t m_stride;                                              // [pair][5][h][pitch] f32, or fp16 when RH
     float2* flow_out; int flow_out_pitch; size_t flow_out_stride;          // optional: write flow_init
 };
 
@@ -403,7 +424,9 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     const void* R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
     float m[5];
     update_px_any<RH>(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, a.w, a.h, x, y, fl.x, fl.y, m);
-    store_m(a.M + (size_t)p * a.m_stride, (unsigned)a.plane_stride, (unsigned)y * (unsigned)a.pitch + (unsigned)x, m);
+    using MT = typename MStore<RH>::type;
+    store_m(static_cast<MT*>(a.M) + (size_t)p * a.m_stride, (unsigned)a.plane_stride,
+            (unsigned)y * (unsigned)a.pitch + (unsigned)x, m);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -416,10 +439,10 @@ constexpr int kBsTW = 32, kBsTH = 8;
 constexpr int kRoiVals = 4;  // sum vx, sum vy, sum mag, count
 
 struct BlurSolveArgs {
-    const float* M; size_t m_stride, plane_stride; int pitch, w, h;
+    const void* M; size_t m_stride, plane_stride; int pitch, w, h;         // f32 planes, or fp16 planes when RH
     // outputs (each optional)
     float2* flow; int flow_pitch; size_t flow_stride;
-    float* Mout;
+    void* Mout;
     const void* R; size_t slot_stride; int slot0, nslots;   // for Mout (fp32 planes, or packed fp16 pixels)
     // ROI reduction (optional): masks [n_roi][h][w] u8; axes per pair; partial [pair][roi][ncta][4]
     const uint8_t* masks; int n_roi; size_t mask_stride; int mask_pitch;
@@ -486,28 +509,29 @@ __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs 
     const int m = wc.m;
     const int x0 = blockIdx.x * kBsTW, y0 = blockIdx.y * kBsTH;
     const int p = blockIdx.z;
-    const float* Mp = a.M + (size_t)p * a.m_stride;
+    using MT = typename MStore<RH>::type;
+    const MT* Mp = static_cast<const MT*>(a.M) + (size_t)p * a.m_stride;
     const int tw = kBsTW + 2 * m;
     const int w = a.w, h = a.h;
     for (int it = threadIdx.x; it < 5 * tw; it += blockDim.x) {
         const int c = it / tw, tx = it - c * tw;
         const int gx = min(max(x0 - m + tx, 0), w - 1);
-        const float* col = Mp + c * a.plane_stride + gx;
+        const MT* col = Mp + c * a.plane_stride + gx;
+        auto at = [&](int row) { return m_to_float(col[(size_t)row * a.pitch]); };
         if (wc.gauss) {
             for (int ty = 0; ty < kBsTH; ++ty) {
                 const int gy = min(y0 + ty, h - 1);
-                float s = col[(size_t)gy * a.pitch] * wc.ker[0];
-                for (int i = 1; i <= m; ++i)
-                    s += (col[(size_t)max(gy - i, 0) * a.pitch] + col[(size_t)min(gy + i, h - 1) * a.pitch]) * wc.ker[i];
+                float s = at(gy) * wc.ker[0];
+                for (int i = 1; i <= m; ++i) s += (at(max(gy - i, 0)) + at(min(gy + i, h - 1))) * wc.ker[i];
                 V[c][ty][tx] = s;
             }
         } else {
             float s = 0.f;
-            for (int i = -m; i <= m; ++i) s += col[(size_t)min(max(y0 + i, 0), h - 1) * a.pitch];
+            for (int i = -m; i <= m; ++i) s += at(min(max(y0 + i, 0), h - 1));
             V[c][0][tx] = s;
             for (int ty = 1; ty < kBsTH; ++ty) {
                 const int gy = y0 + ty;
-                s += col[(size_t)min(gy + m, h - 1) * a.pitch] - col[(size_t)min(max(gy - m - 1, 0), h - 1) * a.pitch];
+                s += at(min(gy + m, h - 1)) - at(min(max(gy - m - 1, 0), h - 1));
                 V[c][ty][tx] = s;
             }
         }
@@ -539,7 +563,8 @@ __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs 
             const void* R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
             float mm[5];
             update_px_any<RH>(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, w, h, x, y, fl.x, fl.y, mm);
-            store_m(a.Mout + (size_t)p * a.m_stride, (unsigned)a.plane_stride, (unsigned)y * (unsigned)a.pitch + (unsigned)x, mm);
+            store_m(static_cast<MT*>(a.Mout) + (size_t)p * a.m_stride, (unsigned)a.plane_stride,
+                    (unsigned)y * (unsigned)a.pitch + (unsigned)x, mm);
         }
     }
     if (a.partial) roi_reduce_store(a, p, x, y, valid, fl, s_red);

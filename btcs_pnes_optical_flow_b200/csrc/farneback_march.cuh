@@ -80,15 +80,16 @@ __global__ void __launch_bounds__(MarchCfg<MH>::NT, 1) k_flow_iter_box(const Mar
         const int gx = x0 - C::HALO + 4 * q;
         const int mode = gx < 0 ? 1 : (gx >= w ? 2 : 0);
         const int cgx = mode == 1 ? 0 : (mode == 2 ? w - 4 : gx);
-        const float* src = a.M + (size_t)p * a.m_stride + (size_t)c * plane + (unsigned)cgx;
+        using MT = typename MStore<RH>::type;
+        const MT* src = static_cast<const MT*>(a.M) + (size_t)p * a.m_stride + (size_t)c * plane + (unsigned)cgx;
         auto ld = [&](int row) -> float4 {                               // row clamped = replicate border
             const int r = min(max(row, 0), h - 1);
-            return __ldg(reinterpret_cast<const float4*>(src + (unsigned)r * pitch));
+            return m_load4(src + (unsigned)r * pitch);
         };
         // Far-ahead L2 prefetch (no registers held): one lane per 128-byte line pulls rows kL2Ahead ahead of the register
         // prefetch queue, so the LDG.128 stream below pays L2 latency, not HBM latency.
         constexpr int kL2Ahead = 40;
-        const bool pf_lane = active && mode == 0 && ((q & 7) == 0);
+        const bool pf_lane = active && mode == 0 && ((q & (RH ? 15 : 7)) == 0);   // one lane per 128-byte line
         auto pf_row = [&](int row) {
             if (pf_lane && row < h) prefetch_l2(src + (unsigned)max(row, 0) * pitch);
         };
@@ -148,7 +149,8 @@ __global__ void __launch_bounds__(MarchCfg<MH>::NT, 1) k_flow_iter_box(const Mar
             R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
         }
         float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
-        float* Mo = a.Mout ? a.Mout + (size_t)p * a.m_stride : nullptr;
+        using MT = typename MStore<RH>::type;
+        MT* Mo = a.Mout ? static_cast<MT*>(a.Mout) + (size_t)p * a.m_stride : nullptr;
         float e00 = 0.f, e01 = 0.f, e10 = 0.f, e11 = 0.f;
         if (a.partial) { const float* ax = a.axes + p * 4; e00 = ax[0]; e01 = ax[1]; e10 = ax[2]; e11 = ax[3]; }
         constexpr int MAXROI = kMarchMaxRoi;
