@@ -12,7 +12,9 @@ dev = torch.device("cuda")
 frames = syn.make_clip(spec, dev, 0, P + 1)
 mask = torch.ones((1080, 1920), dtype=torch.uint8, device=dev)
 plan = B.FlowPlan(1920, 1080, params, max_pairs=16)
-for it in range(14):
+plan.profile(True)
+NIT = int(sys.argv[1]) if len(sys.argv) > 1 else 14
+for it in range(NIT):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -26,6 +28,8 @@ for it in range(14):
     t3 = time.perf_counter()
     print(f"step {it:2d}: launch {1e3*(t1-t0):7.2f} ms  total {1e3*(t2-t0):7.2f} ms  device {e0.elapsed_time(e1):7.2f} ms  d2h {1e3*(t3-t2):5.2f} ms")
 
+pr = plan.profile_read(); print("dominant kernel avg ms", pr["total_ms"] / max(pr["launches"], 1), "launches", pr["launches"])
+if NIT < 14: sys.exit(0)
 print("---- PC1 stage (host band-pass + GPU PC1) on a 2049-sample series")
 n = 2049
 t = np.arange(n) / 30.0
