@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=256, help="frame pairs per GPU per step")
-    ap.add_argument("--max-pairs", type=int, default=16, help="frame pairs per batched kernel launch")
+    ap.add_argument("--max-pairs", type=int, default=64, help="frame pairs per batched kernel launch")
     args = ap.parse_args()
     from btcs_pnes_optical_flow_b200 import synthetic as syn
     spec, params = syn.config_spec("C2")

@@ -353,7 +353,7 @@ int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np,
 template <typename T>
 int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_bytes, int tf, int nf,
                   cudaStream_t st) {
-    if (p->use_fast && p->W * (int)sizeof(float) <= 160 * 1024) {
+    if (p->use_fast && p->W * (int)sizeof(float) * bf::kPyrRows <= 160 * 1024) {
         // level 0: exact 3x3 stencil; coarser levels: one multi-level horizontal pass + per-level vertical pass
         bf::PyrHArgs pa{};
         for (auto& s : p->sc) {
@@ -368,9 +368,10 @@ int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_
             }
         }
         if (pa.nlev > 0) {
-            const size_t smem = (size_t)p->W * sizeof(float);
+            const size_t smem = (size_t)p->W * sizeof(float) * bf::kPyrRows;
             cudaFuncSetAttribute(bf::k_pyr_h_multi<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            bf::k_pyr_h_multi<T><<<dim3(p->H, nf), 256, smem, st>>>(frames, pitch_bytes, frame_bytes, p->W, pa);
+            bf::k_pyr_h_multi<T><<<dim3(cdiv(p->H, bf::kPyrRows), nf), 256, smem, st>>>(frames, pitch_bytes, frame_bytes, p->W,
+                                                                                      p->H, pa);
             LAUNCH_CHECK();
             for (auto& s : p->sc) {
                 if (s.k == 0) continue;

@@ -477,41 +477,76 @@ struct PyrLevelDesc {
 constexpr int kPyrMaxLevels = 15;
 struct PyrHArgs { PyrLevelDesc lv[kPyrMaxLevels]; int nlev; };
 
-// One CTA per (source row, frame): the row is converted to float in shared memory once and every coarser level takes
-// its horizontally blurred + column-interpolated samples from it.
+// One CTA per (kPyrRows source rows, frame): the rows are converted to float in shared memory once (128-bit loads for
+// uint8) and every coarser level takes its horizontally blurred + column-interpolated samples from them; the tap tables
+// (ix, ax, kernel) are read once per output column and applied to all kPyrRows rows.
+constexpr int kPyrRows = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes,
-                                                     int W, const PyrHArgs pa) {
-    extern __shared__ float srow[];                                          // [W]
-    const int r = blockIdx.x, f = blockIdx.y;
-    const T* row = (const T*)((const char*)src + (size_t)f * src_frame_bytes + (size_t)r * src_pitch_bytes);
-    for (int x = threadIdx.x; x < W; x += 256) srow[x] = load_px(row + x);
+                                                     int W, int H, const PyrHArgs pa) {
+    extern __shared__ __align__(16) float srow[];                            // [kPyrRows][W]
+    const int r0 = blockIdx.x * kPyrRows, f = blockIdx.y;
+    const char* fbase = (const char*)src + (size_t)f * src_frame_bytes;
+    const bool vec = (sizeof(T) == 1) && ((W & 15) == 0) && ((src_pitch_bytes & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(fbase) & 15) == 0);
+    for (int rr = 0; rr < kPyrRows; ++rr) {
+        const int r = min(r0 + rr, H - 1);
+        const T* row = (const T*)(fbase + (size_t)r * src_pitch_bytes);
+        float* dstrow = srow + rr * W;
+        if (vec) {
+            for (int x = threadIdx.x * 16; x < W; x += 256 * 16) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(row) + x));
+                const unsigned wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dstrow[x + 4 * k + b] = (float)((wds[k] >> (8 * b)) & 0xffu);
+            }
+        } else {
+            for (int x = threadIdx.x; x < W; x += 256) dstrow[x] = load_px(row + x);
+        }
+    }
     __syncthreads();
     for (int l = 0; l < pa.nlev; ++l) {
         const PyrLevelDesc& d = pa.lv[l];
         const int rad = d.ksize >> 1;
-        float* trow = d.tmp + (size_t)f * d.tmp_frame_stride + (size_t)r * d.tmp_pitch;
+        float* tbase = d.tmp + (size_t)f * d.tmp_frame_stride + (size_t)r0 * d.tmp_pitch;
         for (int x = threadIdx.x; x < d.w; x += 256) {
             const int i0 = d.ix[x];
             const float a = d.ax[x];
-            float b0 = 0.f, b1 = 0.f;
+            float b0[kPyrRows], b1[kPyrRows];
+#pragma unroll
+            for (int rr = 0; rr < kPyrRows; ++rr) b0[rr] = b1[rr] = 0.f;
             if (i0 - rad >= 0 && i0 + 1 + rad < W) {
-                float prev = srow[i0 - rad];
+                float prev[kPyrRows];
+#pragma unroll
+                for (int rr = 0; rr < kPyrRows; ++rr) prev[rr] = srow[rr * W + i0 - rad];
                 for (int j = 0; j < d.ksize; ++j) {
-                    const float nxt = srow[i0 - rad + j + 1];
                     const float kj = __ldg(d.kern + j);
-                    b0 = fmaf(kj, prev, b0);
-                    b1 = fmaf(kj, nxt, b1);
-                    prev = nxt;
+#pragma unroll
+                    for (int rr = 0; rr < kPyrRows; ++rr) {
+                        const float nxt = srow[rr * W + i0 - rad + j + 1];
+                        b0[rr] = fmaf(kj, prev[rr], b0[rr]);
+                        b1[rr] = fmaf(kj, nxt, b1[rr]);
+                        prev[rr] = nxt;
+                    }
                 }
             } else {
-                for (int j = 0; j < d.ksize; ++j) b0 = fmaf(__ldg(d.kern + j), srow[reflect101(i0 - rad + j, W)], b0);
-                if (a != 0.f) {
-                    const int i1 = min(i0 + 1, W - 1);
-                    for (int j = 0; j < d.ksize; ++j) b1 = fmaf(__ldg(d.kern + j), srow[reflect101(i1 - rad + j, W)], b1);
+                const int i1 = min(i0 + 1, W - 1);
+                for (int j = 0; j < d.ksize; ++j) {
+                    const float kj = __ldg(d.kern + j);
+                    const int c0 = reflect101(i0 - rad + j, W), c1 = reflect101(i1 - rad + j, W);
+#pragma unroll
+                    for (int rr = 0; rr < kPyrRows; ++rr) {
+                        b0[rr] = fmaf(kj, srow[rr * W + c0], b0[rr]);
+                        b1[rr] = fmaf(kj, srow[rr * W + c1], b1[rr]);
+                    }
                 }
             }
-            trow[x] = (a != 0.f) ? (b0 * (1.f - a) + b1 * a) : b0;
+#pragma unroll
+            for (int rr = 0; rr < kPyrRows; ++rr)
+                if (r0 + rr < H) tbase[(size_t)rr * d.tmp_pitch + x] = (a != 0.f) ? (b0[rr] * (1.f - a) + b1[rr] * a) : b0[rr];
         }
     }
 }
