@@ -44,6 +44,15 @@ def algorithmic_bytes_per_pair(W, H, S, iters):
     return W * H + S * (28 + 56 * iters)
 
 
+def measured_traffic_per_pair_iteration():
+    """DRAM bytes per pair-iteration of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    p = ROOT / "profiles" / "r1_dominant_kernel.json"
+    try:
+        return float(json.loads(p.read_text())["dram_bytes_per_pair_iteration"])
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -266,8 +275,10 @@ def run_ours(args, spec, params):
         if prof and prof["launches"]:
             bytes_per_pair_iter = 56 * fine["w"] * fine["h"]                   # flow r/w 8+8, R0 20, gathered R1 20
             achieved = prof["pair_iterations"] * bytes_per_pair_iter / (prof["total_ms"] / 1e3) / 1e9
+            tpi = measured_traffic_per_pair_iteration()
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "blur_solve(+update) at the finest scale",
+                    "traffic": (tpi * prof["pair_iterations"] / prof["launches"]) if tpi else None,
+                    "kernel": "k_blur_solve_box<7,RH,24>: blur+solve(+update) at the finest scale",
                     "launches": prof["launches"], "avg_launch_ms": prof["total_ms"] / prof["launches"],
                     "algorithmic_bytes_per_launch": prof["pair_iterations"] * bytes_per_pair_iter / prof["launches"],
                     "kernel_share_of_step": prof["total_ms"] / ms_total, "peak_source": peak_src,
