@@ -7,8 +7,8 @@
 
 One "step" = one pass of the whole hot path over one batch of synthetic input per GPU: `pairs_per_step` frame
 pairs of the config-C2 clip (1920x1080, cv2 default Farneback parameters, full-frame ROI): pyramid -> polynomial
-expansion -> [update matrices + blur + solve] x iterations x scales -> body-axis projection + ROI means (all
-CUDA), gather of the per-frame series to rank 0, host band-pass, sliding-window PCA -> PC1 (CUDA).
+expansion -> [update matrices + blur + solve] x iterations x scales -> body-axis projection + ROI means, gather of
+the per-frame series to rank 0, NaN-robust zero-phase band-pass, sliding-window PCA -> PC1 (all CUDA).
   value  : whole-job pairs/s with the frames already resident in HBM (device timed, max over ranks)
   e2e    : same through the host-buffer API (pinned host frames -> H2D inside the timed region -> series/PC1 D2H)
   roofline: the dominant kernel (fused blur+solve[+update] at the finest scale) timed with CUDA events on its
@@ -196,10 +196,11 @@ def run_ours(args, spec, params):
     sos = pca.butter_bandpass_sos(pca.BPF_LOW_HZ, pca.BPF_HIGH_HZ, spec.fps)
 
     def finish(full):
-        """rank 0: series -> host band-pass -> PC1 on the GPU -> host."""
-        s = full[0].double().cpu().numpy()
-        return pca.dynamic_pc1_sliding(t_all, pca.bandpass_nanrobust(s[:, 0], sos), pca.bandpass_nanrobust(s[:, 1], sos),
-                                       pca.WIN_SEC, pca.STEP_SEC, fs=spec.fps)
+        """rank 0: series -> band-pass -> sliding PCA -> PC1, all on the GPU; only the PC1 waveform comes back."""
+        if not full.is_cuda:
+            full = full.to(dev)
+        s = full[0].double()
+        return pca.flow_to_pc1(None, s[:, 0].contiguous(), s[:, 1].contiguous(), fs_hz=spec.fps).cpu().numpy()
 
     def launch_device():
         """Asynchronous part of a step: flow -> ROI series on the device, gather to rank 0 (NCCL)."""

@@ -8,7 +8,8 @@ host (metrics.py, mirrors optical_PC1.py).
 from .flow import (FB_PARAMS, FlowPlan, BtcsFlowError, Cv2CompatError, OPTFLOW_FARNEBACK_GAUSSIAN,
                    OPTFLOW_USE_INITIAL_FLOW, build_roi_mask, calcOpticalFlowFarneback, clear_plans,
                    compute_roi_mean_body_flow, get_plan, run_body_axis_flow_core, skel_index_from_time)
-from .pca import bandpass_nanrobust, butter_bandpass_sos, dynamic_pc1_sliding, flow_to_pc1, pc1_sliding_batched
+from .pca import (bandpass_nanrobust, bandpass_nanrobust_device, butter_bandpass_sos, dynamic_pc1_sliding, flow_to_pc1,
+                  pc1_sliding_batched)
 from .metrics import compute_pc1_metrics
 
 __version__ = "0.1.0"

@@ -17,6 +17,7 @@
 #include "farneback_fast.cuh"
 #include "farneback_march.cuh"
 #include "pc1_kernels.cuh"
+#include "bandpass_kernels.cuh"
 
 namespace {
 
@@ -947,6 +948,68 @@ int bf_pc1_sliding_host(const double* vx, const double* vy, int n, int win_n, in
     }
     cudaFree(d);
     return rc;
+}
+
+// ---- band-pass -------------------------------------------------------------------------------------------
+
+int bf_sosfilt_zi(const double* sos, int n_sections, double* zi) {
+    if (!sos || !zi || n_sections < 1) return fail(BF_E_INVALID, "bad arguments");
+    // scipy.signal.sosfilt_zi: per-section lfilter_zi (steady state of the step response), scaled by the DC gain of the
+    // sections before it
+    double scale = 1.0;
+    for (int s = 0; s < n_sections; ++s) {
+        const double* q = sos + 6 * s;
+        const double a0 = q[3];
+        if (a0 == 0.0) return fail(BF_E_INVALID, "sos[%d].a0 is zero", s);
+        const double b0 = q[0] / a0, b1 = q[1] / a0, b2 = q[2] / a0, a1 = q[4] / a0, a2 = q[5] / a0;
+        const double Bsum = (b1 - a1 * b0) + (b2 - a2 * b0);
+        const double z0 = Bsum / ((1.0 + a1) + a2);
+        const double z1 = (1.0 + a1) * z0 - (b1 - a1 * b0);
+        zi[2 * s] = scale * z0;
+        zi[2 * s + 1] = scale * z1;
+        scale *= (q[0] + q[1] + q[2]) / (q[3] + q[4] + q[5]);
+    }
+    return 0;
+}
+
+int bf_bandpass_nanrobust(const double* x, int n_series, int n, const double* sos, const double* zi, int n_sections,
+                          double* y, void* stream) {
+    if (!x || !y || !sos) return fail(BF_E_INVALID, "NULL pointer");
+    if (n_series < 1 || n < 0) return fail(BF_E_INVALID, "bad sizes");
+    if (n_sections < 1 || n_sections > bf::kMaxSections) return fail(BF_E_UNSUPPORTED, "1..%d second-order sections supported", bf::kMaxSections);
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    bf::SosCoef c{};
+    c.n_sections = n_sections;
+    std::vector<double> zloc(2 * n_sections);
+    if (!zi) {
+        int rc = bf_sosfilt_zi(sos, n_sections, zloc.data());
+        if (rc) return rc;
+        zi = zloc.data();
+    }
+    for (int s = 0; s < n_sections; ++s) {
+        const double* q = sos + 6 * s;
+        if (q[3] == 0.0) return fail(BF_E_INVALID, "sos[%d].a0 is zero", s);
+        c.b0[s] = q[0] / q[3]; c.b1[s] = q[1] / q[3]; c.b2[s] = q[2] / q[3]; c.a1[s] = q[4] / q[3]; c.a2[s] = q[5] / q[3];
+        c.zi0[s] = zi[2 * s]; c.zi1[s] = zi[2 * s + 1];
+    }
+    // same length rules as the reference: sos_required_padlen = 3 * (2 * n_sections) (optical_PCA.py:74-80, 107, 114)
+    const int max_pad = 3 * (2 * n_sections), min_len = max_pad + 1;
+    struct Scratch { double* buf = nullptr; size_t cap = 0; int dev = -1; };
+    static thread_local Scratch sc;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const int stride = n + 2 * max_pad + 8;
+    const size_t need = (size_t)n_series * stride;
+    if (sc.dev != dev || sc.cap < need) {
+        if (sc.buf) { CU(cudaDeviceSynchronize()); cudaFree(sc.buf); sc.buf = nullptr; sc.cap = 0; }
+        CU(cudaMalloc((void**)&sc.buf, (need + need / 2) * sizeof(double)));
+        sc.cap = need + need / 2;
+        sc.dev = dev;
+    }
+    bf::k_bandpass_nanrobust<<<n_series, 32, 0, st>>>(x, n, c, min_len, max_pad, y, sc.buf, stride);
+    LAUNCH_CHECK();
+    return 0;
 }
 
 // ---- stage-level entry points ---------------------------------------------------------------------------

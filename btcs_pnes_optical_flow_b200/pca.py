@@ -1,8 +1,10 @@
 """Host-side mirror of the reference's PCA stage (/root/reference/optical_PCA.py) over libbtcsflow.so.
 
-dynamic_pc1_sliding (optical_PCA.py:136-235) runs on the GPU (bf_pc1_sliding*); the NaN-robust zero-phase
-band-pass that precedes it (optical_PCA.py:64-121) is O(T) host signal processing with scipy and stays on
-the host in this round.
+dynamic_pc1_sliding (optical_PCA.py:136-235) runs on the GPU (bf_pc1_sliding*).  The NaN-robust zero-phase
+band-pass that precedes it (optical_PCA.py:64-121) exists twice: `bandpass_nanrobust` is the reference's host version
+(scipy.signal.sosfiltfilt per finite run) and `bandpass_nanrobust_device` the same arithmetic on the GPU
+(bf_bandpass_nanrobust), so a flow series can go to PC1 without a host hop (`flow_to_pc1`).
+The Butterworth design itself (scipy.signal.butter, once per run) stays on the host.
 """
 from __future__ import annotations
 
@@ -117,10 +119,52 @@ def bandpass_nanrobust(x: np.ndarray, sos: np.ndarray) -> np.ndarray:
     return y
 
 
+def bandpass_nanrobust_device(x, sos: np.ndarray):
+    """bandpass_nanrobust (optical_PCA.py:96-121) on the GPU: scipy.signal.sosfiltfilt per contiguous finite run,
+    same length rules.  x: [n] or [n_series, n], numpy (returns numpy) or a torch CUDA tensor (stays on the device)."""
+    import torch
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.BtcsFlowError(_lib.BF_E_NODEVICE, "no CUDA device: bandpass_nanrobust_device has no CPU fallback")
+    sos = np.ascontiguousarray(sos, np.float64)
+    if sos.ndim != 2 or sos.shape[1] != 6:
+        raise Cv2CompatError(-1, "sos must have shape (n_sections, 6)")
+    is_torch = type(x).__module__.startswith("torch")
+    dx = x.to(torch.float64) if is_torch else torch.from_numpy(np.ascontiguousarray(x, np.float64)).cuda()
+    one_d = dx.dim() == 1
+    dx = (dx[None] if one_d else dx).contiguous()
+    out = torch.empty_like(dx)
+    check(lib.bf_bandpass_nanrobust(dx.data_ptr(), dx.shape[0], dx.shape[1], sos.ctypes.data, None, sos.shape[0],
+                                    out.data_ptr(), torch.cuda.current_stream(dx.device).cuda_stream))
+    out = out[0] if one_d else out
+    return out if is_torch else out.cpu().numpy()
+
+
+def sosfilt_zi(sos: np.ndarray) -> np.ndarray:
+    """scipy.signal.sosfilt_zi through the C library (host arithmetic; no GPU needed)."""
+    sos = np.ascontiguousarray(sos, np.float64)
+    zi = np.empty((sos.shape[0], 2), np.float64)
+    check(_lib.load().bf_sosfilt_zi(sos.ctypes.data, sos.shape[0], zi.ctypes.data))
+    return zi
+
+
 def flow_to_pc1(t, vx, vy, fs_hz: float = fs, win_sec: float = WIN_SEC, step_sec: float = STEP_SEC,
-                low_hz: float = BPF_LOW_HZ, high_hz: float = BPF_HIGH_HZ, order: int = BPF_ORDER) -> np.ndarray:
-    """Band-pass + dynamic PC1 for one series: the body of optical_PCA.main (optical_PCA.py:254-267)."""
+                low_hz: float = BPF_LOW_HZ, high_hz: float = BPF_HIGH_HZ, order: int = BPF_ORDER,
+                on_device: bool = True):
+    """Band-pass + dynamic PC1 for one series: the body of optical_PCA.main (optical_PCA.py:254-267).
+
+    on_device=True (default) runs the band-pass on the GPU too, so a torch CUDA series never leaves the device;
+    on_device=False uses scipy on the host for the band-pass exactly like the reference."""
     sos = butter_bandpass_sos(low_hz, high_hz, fs_hz, order=order)
+    if on_device:
+        import torch
+        is_torch = type(vx).__module__.startswith("torch")
+        dvx = vx if is_torch else torch.from_numpy(np.ascontiguousarray(vx, np.float64)).cuda()
+        dvy = vy if is_torch else torch.from_numpy(np.ascontiguousarray(vy, np.float64)).cuda()
+        both = bandpass_nanrobust_device(torch.stack([dvx.to(torch.float64), dvy.to(torch.float64)]), sos)
+        win_n, step_n = window_samples(win_sec, step_sec, fs_hz)
+        out = pc1_sliding_batched(both[0:1], both[1:2], [win_n], [step_n], (0.0, 1.0))[0, 0]
+        return out if is_torch else out.cpu().numpy()
     return dynamic_pc1_sliding(t, bandpass_nanrobust(vx, sos), bandpass_nanrobust(vy, sos), win_sec, step_sec,
                                np.array([0.0, 1.0]), fs=fs_hz)
 

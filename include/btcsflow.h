@@ -134,6 +134,18 @@ int bf_pc1_sliding_batched(const double* vx, const double* vy, int n_series, int
 int bf_pc1_sliding_host(const double* vx, const double* vy, int n, int win_n, int step_n, double ref_x,
                         double ref_y, int min_samples, double* pc1_out);
 
+/* ---- NaN-robust zero-phase band-pass (replaces bandpass_nanrobust, optical_PCA.py:96-121) ------------- */
+
+/* x, y: float64 [n_series, n] on the device (NaN allowed).  sos: HOST float64 [n_sections, 6] in scipy layout
+ * (b0 b1 b2 a0 a1 a2), e.g. scipy.signal.butter(..., output="sos") as at optical_PCA.py:64-71.  zi: HOST float64
+ * [n_sections, 2] = scipy.signal.sosfilt_zi(sos), or NULL to have it computed here (bf_sosfilt_zi).  Every contiguous
+ * finite run of at least 3*(2*n_sections)+1 samples is filtered like scipy.signal.sosfiltfilt(sos, run, padlen =
+ * min(3*(2*n_sections), len/2 - 1)); everything else stays NaN. */
+int bf_bandpass_nanrobust(const double* x, int n_series, int n, const double* sos, const double* zi, int n_sections,
+                          double* y, void* stream);
+/* scipy.signal.sosfilt_zi for host callers without scipy: zi [n_sections, 2]. */
+int bf_sosfilt_zi(const double* sos, int n_sections, double* zi);
+
 /* ---- stage-level entry points (kernel-by-kernel parity; device pointers) ----------------------------- */
 
 /* Pyramid level i of the plan from one full-resolution frame -> float32 [h_i, w_i] contiguous. */

@@ -113,3 +113,38 @@ def test_end_to_end_against_live_cv2():
     assert np.sign(a["Kendall_tau_0_10"]) == np.sign(b["Kendall_tau_0_10"]) and b["Kendall_tau_0_10"] > 0.3
     assert abs(a["ADS_slope_0_10"] / b["ADS_slope_0_10"] - 1) < 1e-3
     assert abs(a["PC1_area_0_10"] / b["PC1_area_0_10"] - 1) < 1e-3
+
+
+def test_device_bandpass_matches_scipy(golden):
+    """bandpass_nanrobust on the GPU against the reference's outputs (golden) and the scipy host version."""
+    import torch
+    from btcs_pnes_optical_flow_b200 import pca
+    g = golden("pc1_golden.npz")
+    sos = pca.butter_bandpass_sos(0.5, 5.0, 30, order=4)
+    x = np.stack([g[f"vx{s}"] for s in range(3)])
+    got = pca.bandpass_nanrobust_device(x, sos)
+    for s in range(3):
+        ref = g[f"bp_vx{s}"]                                                  # output of the reference function itself
+        assert np.array_equal(np.isnan(got[s]), np.isnan(ref))
+        assert np.nanmax(np.abs(got[s] - ref)) < 1e-12, np.nanmax(np.abs(got[s] - ref))
+    rng = np.random.default_rng(5)
+    for n, order, band, fs in ((9000, 4, (0.5, 5.0), 30.0), (1234, 2, (1.0, 8.0), 60.0), (40, 4, (0.5, 5.0), 30.0),
+                                (25, 4, (0.5, 5.0), 30.0), (24, 4, (0.5, 5.0), 30.0), (3000, 6, (0.3, 4.0), 25.0)):
+        sos = pca.butter_bandpass_sos(band[0], band[1], fs, order=order)
+        v = np.cumsum(rng.standard_normal(n)) * 0.1 + np.sin(np.arange(n) * 0.4)
+        v[0] = np.nan
+        for _ in range(4):
+            a = int(rng.integers(0, n))
+            v[a:a + int(rng.integers(1, 40))] = np.nan
+        ref = pca.bandpass_nanrobust(v, sos)
+        dev = pca.bandpass_nanrobust_device(torch.from_numpy(v).cuda(), sos)
+        assert dev.is_cuda
+        out = dev.cpu().numpy()
+        assert np.array_equal(np.isnan(out), np.isnan(ref)), (n, order)
+        if np.isfinite(ref).any():
+            assert np.nanmax(np.abs(out - ref)) < 1e-11 * max(1.0, np.nanmax(np.abs(ref))), (n, order, np.nanmax(np.abs(out - ref)))
+    # whole tail on the device == host band-pass + device PC1
+    t = g["t"]
+    a = pca.flow_to_pc1(t, g["vx0"], g["vy0"], on_device=True)
+    b = pca.flow_to_pc1(t, g["vx0"], g["vy0"], on_device=False)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.nanmax(np.abs(a - b)) < 1e-11

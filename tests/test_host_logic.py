@@ -82,3 +82,14 @@ def test_synthetic_clip_is_deterministic_and_moves():
     for name in ("C1", "C2", "C3", "C4", "C5"):
         s, p = synthetic.config_spec(name)
         assert set(p) == set(B.FB_PARAMS)
+
+
+def test_sosfilt_zi_matches_scipy():
+    """bf_sosfilt_zi is host arithmetic inside the C library (no GPU): must equal scipy.signal.sosfilt_zi."""
+    from scipy.signal import butter, sosfilt_zi
+    from btcs_pnes_optical_flow_b200 import pca
+    for order, band, fs in ((4, (0.5, 5.0), 30.0), (2, (1.0, 8.0), 60.0), (6, (0.3, 4.0), 25.0)):
+        sos = butter(order, [band[0] / (fs / 2), band[1] / (fs / 2)], btype="band", output="sos")
+        assert np.allclose(pca.sosfilt_zi(sos), sosfilt_zi(sos), rtol=1e-12, atol=1e-14)
+    sos = butter(3, 0.2, output="sos")                                       # low-pass: non-zero DC gain chain
+    assert np.allclose(pca.sosfilt_zi(sos), sosfilt_zi(sos), rtol=1e-12, atol=1e-14)
