@@ -369,7 +369,7 @@ int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_
             }
         }
         if (pa.nlev > 0) {
-            const size_t smem = (size_t)p->W * sizeof(float) * bf::kPyrRows;
+            const size_t smem = (size_t)(p->W + (p->W >> 5) + 1) * sizeof(float) * bf::kPyrRows;
             cudaFuncSetAttribute(bf::k_pyr_h_multi<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             bf::k_pyr_h_multi<T><<<dim3(cdiv(p->H, bf::kPyrRows), nf), 256, smem, st>>>(frames, pitch_bytes, frame_bytes, p->W,
                                                                                       p->H, pa);

@@ -485,7 +485,11 @@ constexpr int kPyrRows = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes,
                                                      int W, int H, const PyrHArgs pa) {
-    extern __shared__ __align__(16) float srow[];                            // [kPyrRows][W]
+    // [kPyrRows][WP], element i of a row lives at i + (i >> 5): one pad word per 32 makes the power-of-two strides of the
+    // decimating levels (lanes 2, 4, 8 ... source pixels apart) bank-conflict free
+    extern __shared__ __align__(16) float srow[];
+    const int WP = W + (W >> 5) + 1;
+    auto sx = [](int i) { return i + (i >> 5); };
     const int r0 = blockIdx.x * kPyrRows, f = blockIdx.y;
     const char* fbase = (const char*)src + (size_t)f * src_frame_bytes;
     const bool vec = (sizeof(T) == 1) && ((W & 15) == 0) && ((src_pitch_bytes & 15) == 0) &&
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, 
     for (int rr = 0; rr < kPyrRows; ++rr) {
         const int r = min(r0 + rr, H - 1);
         const T* row = (const T*)(fbase + (size_t)r * src_pitch_bytes);
-        float* dstrow = srow + rr * W;
+        float* dstrow = srow + rr * WP;
         if (vec) {
             for (int x = threadIdx.x * 16; x < W; x += 256 * 16) {
                 const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(row) + x));
@@ -501,10 +505,10 @@ __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, 
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) dstrow[x + 4 * k + b] = (float)((wds[k] >> (8 * b)) & 0xffu);
+                    for (int b = 0; b < 4; ++b) dstrow[sx(x + 4 * k + b)] = (float)((wds[k] >> (8 * b)) & 0xffu);
             }
         } else {
-            for (int x = threadIdx.x; x < W; x += 256) dstrow[x] = load_px(row + x);
+            for (int x = threadIdx.x; x < W; x += 256) dstrow[sx(x)] = load_px(row + x);
         }
     }
     __syncthreads();
@@ -521,12 +525,13 @@ __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, 
             if (i0 - rad >= 0 && i0 + 1 + rad < W) {
                 float prev[kPyrRows];
 #pragma unroll
-                for (int rr = 0; rr < kPyrRows; ++rr) prev[rr] = srow[rr * W + i0 - rad];
+                for (int rr = 0; rr < kPyrRows; ++rr) prev[rr] = srow[rr * WP + sx(i0 - rad)];
                 for (int j = 0; j < d.ksize; ++j) {
                     const float kj = __ldg(d.kern + j);
+                    const int cn = sx(i0 - rad + j + 1);
 #pragma unroll
                     for (int rr = 0; rr < kPyrRows; ++rr) {
-                        const float nxt = srow[rr * W + i0 - rad + j + 1];
+                        const float nxt = srow[rr * WP + cn];
                         b0[rr] = fmaf(kj, prev[rr], b0[rr]);
                         b1[rr] = fmaf(kj, nxt, b1[rr]);
                         prev[rr] = nxt;
@@ -536,11 +541,11 @@ __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, 
                 const int i1 = min(i0 + 1, W - 1);
                 for (int j = 0; j < d.ksize; ++j) {
                     const float kj = __ldg(d.kern + j);
-                    const int c0 = reflect101(i0 - rad + j, W), c1 = reflect101(i1 - rad + j, W);
+                    const int c0 = sx(reflect101(i0 - rad + j, W)), c1 = sx(reflect101(i1 - rad + j, W));
 #pragma unroll
                     for (int rr = 0; rr < kPyrRows; ++rr) {
-                        b0[rr] = fmaf(kj, srow[rr * W + c0], b0[rr]);
-                        b1[rr] = fmaf(kj, srow[rr * W + c1], b1[rr]);
+                        b0[rr] = fmaf(kj, srow[rr * WP + c0], b0[rr]);
+                        b1[rr] = fmaf(kj, srow[rr * WP + c1], b1[rr]);
                     }
                 }
             }
