@@ -302,7 +302,7 @@ int launch_update(const bf::UpdateArgs& a, int np, bool r_half, cudaStream_t st)
 
 // Which kernel runs one blur+solve(+update) iteration: the tile kernel (default), the warp-specialised strip-marching
 // kernel (BTCSFLOW_KERNEL=march), or the runtime-parameter kernel (BTCSFLOW_NO_FAST=1 / unsupported parameters).
-enum BlurKernel { BK_GENERIC = 0, BK_TILE = 1, BK_MARCH = 2 };
+enum BlurKernel { BK_GENERIC = 0, BK_TILE = 1, BK_MARCH = 2, BK_GAUSS = 3 };
 
 int sm_count_cached() {
     static int n = 0;
@@ -318,6 +318,7 @@ BlurKernel choose_blur_kernel(const bf::BlurSolveArgs& a, const bf::WinCoef& wc,
     if (!allow_fast) return BK_GENERIC;
     const char* e = getenv("BTCSFLOW_KERNEL");                      // read per call: tests flip it within a process
     const int pref = (e && strcmp(e, "march") == 0) ? BK_MARCH : BK_TILE;   // tile kernel measured faster (profiles/)
+    if (bf::gauss_fast_supported(wc)) return BK_GAUSS;              // winsize 20/21 Gaussian window (config C4)
     if (pref == BK_MARCH && bf::march_supported(wc, a)) return BK_MARCH;
     if (bf::blur_solve_fast_supported(wc, a.pitch) && bf::blur_solve_fast_aligned(a)) return BK_TILE;
     return BK_GENERIC;
@@ -327,6 +328,7 @@ int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, b
     switch (choose_blur_kernel(a, wc, allow_fast)) {
         case BK_MARCH: return bf::march_ncta(a.w, a.h, np, sm_count_cached());
         case BK_TILE: return bf::blur_solve_fast_ncta(a.w, a.h);
+        case BK_GAUSS: return bf::gauss_fast_ncta(a.w, a.h);
         default: return cdiv(a.w, bf::kBsTW) * cdiv(a.h, bf::kBsTH);
     }
 }
@@ -339,6 +341,9 @@ int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np,
             break;
         case BK_TILE:
             bf::launch_blur_solve_fast(a, wc, np, r_half, st);
+            break;
+        case BK_GAUSS:
+            bf::launch_gauss_fast(a, wc, np, r_half, st);
             break;
         default: {
             dim3 g(cdiv(a.w, bf::kBsTW), cdiv(a.h, bf::kBsTH), np);

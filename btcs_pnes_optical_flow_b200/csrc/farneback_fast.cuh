@@ -268,6 +268,187 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// k_blur_solve_gauss<MH>: the same fused iteration for OPTFLOW_FARNEBACK_GAUSSIAN (separable float32
+// Gaussian window, sigma = 0.3*MH, replicate borders) -- config C4 runs winsize 21 (MH = 10).  No running sums here:
+// every output is a (2MH+1)-tap weighted sum.  Phase 1 walks one scalar column per thread with the (2MH+1)-row window in
+// registers (fully unrolled static ring); phase 2 reads 4+2MH values per channel with LDS.128 and evaluates 4 outputs;
+// summation order is cv2's: centre tap first, then symmetric pairs (x[-i] + x[+i]) * ker[i].
+// ---------------------------------------------------------------------------------------------------
+template <int MH, int TH>
+struct FastGaussCfg {
+    static constexpr int HALO = (MH + 3) / 4 * 4;
+    static constexpr int D = HALO - MH;
+    static constexpr int NCOL = kFbTW + 2 * HALO;
+    static constexpr int VP = NCOL + 4;
+    static constexpr int WIN = 2 * MH + 1;
+    static constexpr int NCH = (D + 2 * MH + 3) / 4 + 1;
+    static constexpr int RG = TH / 8;
+    static constexpr int V_FLOATS = 5 * TH * VP;
+    static constexpr size_t SMEM = (size_t)(V_FLOATS + 64) * sizeof(float);
+    static_assert(TH % 8 == 0, "tile height must be a multiple of 8");
+    static_assert((size_t)TH * kFbTW * sizeof(float2) <= (size_t)V_FLOATS * sizeof(float), "F must fit in V");
+};
+
+template <int MH, bool RH, int TH>
+__global__ void __launch_bounds__(256, 2) k_blur_solve_gauss(const BlurSolveArgs a, const WinCoef wc) {
+    using C = FastGaussCfg<MH, TH>;
+    using MT = typename MStore<RH>::type;
+    extern __shared__ __align__(16) float smem[];
+    float* V = smem;
+    float2* F = reinterpret_cast<float2*>(smem);
+    float* s_red = smem + C::V_FLOATS;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * TH, p = blockIdx.z;
+    const int w = a.w, h = a.h;
+    const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
+    const MT* Mp = static_cast<const MT*>(a.M) + (size_t)p * a.m_stride;
+    float ker[MH + 1];
+#pragma unroll
+    for (int i = 0; i <= MH; ++i) ker[i] = wc.ker[i];
+
+    const void* R0 = nullptr;
+    const void* R1 = nullptr;
+    if (a.Mout) {
+        R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
+        R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
+        prefetch_r_block<RH>(R0, R1, plane, pitch, w, h, x0, y0, TH, tid, 256);
+    }
+
+    // ---------------- phase 1: vertical Gaussian, one scalar column per task ----------------
+    for (int task = tid; task < 5 * C::NCOL; task += 256) {
+        const int c = task / C::NCOL, col = task - c * C::NCOL;
+        const int gx = min(max(x0 - C::HALO + col, 0), w - 1);
+        const MT* src = Mp + (size_t)c * plane + (unsigned)gx;
+        float* dst = V + (size_t)c * TH * C::VP + col;
+        auto ld = [&](int i) -> float {                               // row y0 - MH + i, clamped (replicate)
+            const int r = min(max(y0 - MH + i, 0), h - 1);
+            return m_to_float(__ldg(src + (unsigned)r * pitch));
+        };
+        float win[C::WIN];
+#pragma unroll
+        for (int i = 0; i < C::WIN; ++i) win[i] = ld(i);
+#pragma unroll
+        for (int j = 0; j < TH; ++j) {
+            // window of output row j: ring slots (j + k) % WIN for k = 0 .. 2MH, centre k = MH
+            float sacc = win[(j + MH) % C::WIN] * ker[0];
+#pragma unroll
+            for (int i = 1; i <= MH; ++i) sacc += (win[(j + MH - i) % C::WIN] + win[(j + MH + i) % C::WIN]) * ker[i];
+            dst[j * C::VP] = sacc;
+            if (j + 1 < TH) win[j % C::WIN] = ld(j + C::WIN);         // row leaving the window is replaced by the next one
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: horizontal Gaussian + solve ----------------
+    const int g = tid & 31, rb = tid >> 5;
+    float2 fl[C::RG][4];
+#pragma unroll
+    for (int k = 0; k < C::RG; ++k) {
+        const int r = rb + 8 * k;
+        float gs[5][4];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float4* vp = reinterpret_cast<const float4*>(V + ((size_t)c * TH + r) * C::VP) + g;
+            float vv[4 * C::NCH];
+#pragma unroll
+            for (int i = 0; i < C::NCH; ++i) {
+                const float4 q4 = vp[i];
+                vv[4 * i] = q4.x; vv[4 * i + 1] = q4.y; vv[4 * i + 2] = q4.z; vv[4 * i + 3] = q4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = C::HALO + j;
+                float sacc = vv[ci] * ker[0];
+#pragma unroll
+                for (int i = 1; i <= MH; ++i) sacc += (vv[ci - i] + vv[ci + i]) * ker[i];
+                gs[c][j] = sacc;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float g11 = gs[0][j], g12 = gs[1][j], g22 = gs[2][j], h1 = gs[3][j], h2 = gs[4][j];
+            const float idet = 1.f / (diff_of_products(g11, g22, g12, g12) + 1e-3f);
+            fl[k][j].x = diff_of_products(g11, h2, g12, h1) * idet;
+            fl[k][j].y = diff_of_products(g22, h1, g12, h2) * idet;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < C::RG; ++k) {
+        float4* fp = reinterpret_cast<float4*>(F + (rb + 8 * k) * kFbTW + 4 * g);
+        fp[0] = make_float4(fl[k][0].x, fl[k][0].y, fl[k][1].x, fl[k][1].y);
+        fp[1] = make_float4(fl[k][2].x, fl[k][2].y, fl[k][3].x, fl[k][3].y);
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: coalesced tail (same as the box kernel) ----------------
+    const int lane = tid & 31, wid = tid >> 5;
+    if (a.flow || a.Mout) {
+        float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
+        MT* Mo = a.Mout ? static_cast<MT*>(a.Mout) + (size_t)p * a.m_stride : nullptr;
+#pragma unroll 4
+        for (int i = 0; i < 4 * C::RG; ++i) {
+            const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
+            const int x = x0 + cx, y = y0 + r;
+            if (x < w && y < h) {
+                const float2 f = F[r * kFbTW + cx];
+                if (fo) fo[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x] = f;
+                if (Mo) {
+                    float mm[5];
+                    update_px_any<RH>(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
+                    store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, mm);
+                }
+            }
+        }
+    }
+    if (a.partial) {
+        const float* ax = a.axes + p * 4;
+        const float e00 = ax[0], e01 = ax[1], e10 = ax[2], e11 = ax[3];
+        const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+        for (int roi = 0; roi < a.n_roi; ++roi) {
+            const uint8_t* mk = a.masks + (size_t)roi * a.mask_stride;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < 4 * C::RG; ++i) {
+                const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
+                const int x = x0 + cx, y = y0 + r;
+                if (x < w && y < h && mk[(size_t)y * a.mask_pitch + x] != 0) {
+                    const float2 f = F[r * kFbTW + cx];
+                    const float vx = f.x * e00 + f.y * e01;
+                    const float vy = f.x * e10 + f.y * e11;
+                    s0 += vx; s1 += vy; s2 += sqrtf(vx * vx + vy * vy); s3 += 1.f;
+                }
+            }
+            s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+            __syncthreads();
+            if (lane == 0) { s_red[wid * 4] = s0; s_red[wid * 4 + 1] = s1; s_red[wid * 4 + 2] = s2; s_red[wid * 4 + 3] = s3; }
+            __syncthreads();
+            if (tid < 4) {
+                float t = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t += s_red[i * 4 + tid];
+                a.partial[(((size_t)p * a.n_roi + roi) * ncta + cta) * kRoiVals + tid] = t;
+            }
+        }
+    }
+}
+
+constexpr int kGaussTH = 32;
+inline bool gauss_fast_supported(const WinCoef& wc) { return wc.gauss && wc.m == 10; }
+inline int gauss_fast_ncta(int w, int h) { return ((w + kFbTW - 1) / kFbTW) * ((h + kGaussTH - 1) / kGaussTH); }
+template <bool RH>
+inline void launch_gauss_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
+    using C = FastGaussCfg<10, kGaussTH>;
+    cudaFuncSetAttribute(k_blur_solve_gauss<10, RH, kGaussTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    dim3 g((a.w + kFbTW - 1) / kFbTW, (a.h + kGaussTH - 1) / kGaussTH, np);
+    k_blur_solve_gauss<10, RH, kGaussTH><<<g, 256, C::SMEM, st>>>(a, wc);
+}
+inline void launch_gauss_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st) {
+    if (r_half) launch_gauss_fast_t<true>(a, wc, np, st);
+    else launch_gauss_fast_t<false>(a, wc, np, st);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 inline bool blur_solve_fast_supported(const WinCoef& wc, int pitch) {

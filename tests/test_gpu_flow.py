@@ -164,3 +164,20 @@ def test_1080p_full_size_properties():
     inner = got[100:-100, 100:-100]
     assert abs(inner[..., 0].mean() - 2.25) < 0.05 and abs(inner[..., 1].mean() + 1.5) < 0.05
     assert np.array_equal(got, B.calcOpticalFlowFarneback(a, b, None, **B.FB_PARAMS))
+
+
+def test_4k_gaussian_config_full_size():
+    """BASELINE config C4 at full size: 3840x2160, OPTFLOW_FARNEBACK_GAUSSIAN, poly_n 7, sigma 1.5, winsize 21, levels 5
+    (6 scales down to 120x68) -- one pair against cv2 (the specialised Gaussian-window kernel runs here)."""
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    p = dict(pyr_scale=0.5, levels=5, winsize=21, iterations=3, poly_n=7, poly_sigma=1.5, flags=256)
+    a, b = textured(2160, 3840, 31), textured(2160, 3840, 31, shift=(3.4, -2.2))
+    with B.FlowPlan(3840, 2160, p, max_pairs=1) as plan:
+        assert [(s["w"], s["h"]) for s in plan.scales()][0] == (120, 68)
+        got = plan.flow_pair(a, b)
+    ref = cv2_ref.farneback(a, b, **p)
+    mean, mx = epe(got, ref)
+    assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (mean, mx)
+    inner = got[200:-200, 200:-200]
+    assert abs(inner[..., 0].mean() - 3.4) < 0.05 and abs(inner[..., 1].mean() + 2.2) < 0.05
