@@ -56,10 +56,12 @@ __device__ __forceinline__ void vertical_box_sums(const MT* __restrict__ src, un
         return m_load4(src + (unsigned)r * pitch);
     };
     auto st = [&](int j, const float4& s) {
-        float4 o = s;
-        if (mode == 1) o = make_float4(s.x, s.x, s.x, s.x);
-        else if (mode == 2) o = make_float4(s.w, s.w, s.w, s.w);
-        *reinterpret_cast<float4*>(dst + j * vp) = o;
+        if (mode == 0) {                                  // branch, not 4 selects per store: only edge columns differ
+            *reinterpret_cast<float4*>(dst + j * vp) = s;
+        } else {
+            const float e = mode == 1 ? s.x : s.w;
+            *reinterpret_cast<float4*>(dst + j * vp) = make_float4(e, e, e, e);
+        }
     };
     float4 win[WIN];
 #pragma unroll
@@ -82,36 +84,41 @@ __device__ __forceinline__ void vertical_box_sums(const MT* __restrict__ src, un
     }
 }
 
-// Lines of R that a block of rows [ya, ya+nrows) x columns [x0, x0+128) will touch in its update tail: R0 under the
-// block, R1 within +-2 rows / +-32 columns (larger flows simply miss).  Requested into L2 ahead of use.
-template <bool RH>
+// Lines of R that a block of rows [ya, ya+NROWS) x columns [x0, x0+128) will touch in its update tail: R0 under the
+// block, R1 within +-2 rows / +-32 columns (larger flows simply miss).  Requested into L2 ahead of use.  The index math
+// is kept to shifts and constant divisions: these loops used to cost ~25 instructions per pixel (ncu, profiles/).
+template <bool RH, int NROWS>
 __device__ __forceinline__ void prefetch_r_block(const void* R0v, const void* R1v, unsigned plane, unsigned pitch, int w, int h,
-                                                 int x0, int ya, int nrows, int tid, int nthreads) {
+                                                 int x0, int ya, int tid, int nthreads) {
     if (RH) {
         const uint4* R0 = static_cast<const uint4*>(R0v);
         const uint4* R1 = static_cast<const uint4*>(R1v);
-        const int xmax = max(w - 1, 0);                                  // 8 pixels per 128-byte line
-        for (int e = tid; e < nrows * 16; e += nthreads) {
+        const int xmax = max(w - 1, 0);                                  // 8 pixels per 128-byte line, 16 lines per row
+        for (int e = tid; e < NROWS * 16; e += nthreads) {
             const int yy = min(ya + (e >> 4), h - 1), xx = min(x0 + (e & 15) * 8, xmax);
             prefetch_l2(R0 + (unsigned)yy * pitch + (unsigned)xx);
         }
-        for (int e = tid; e < (nrows + 4) * 24; e += nthreads) {
-            const int yy = min(max(ya - 2 + e / 24, 0), h - 1), xx = min(max(x0 - 32 + (e % 24) * 8, 0), xmax);
+        for (int e = tid; e < (NROWS + 4) * 24; e += nthreads) {
+            const int r = e / 24, l = e - r * 24;
+            const int yy = min(max(ya - 2 + r, 0), h - 1), xx = min(max(x0 - 32 + l * 8, 0), xmax);
             prefetch_l2(R1 + (unsigned)yy * pitch + (unsigned)xx);
         }
     } else {
         const float* R0 = static_cast<const float*>(R0v);
         const float* R1 = static_cast<const float*>(R1v);
         const int xmax = (int)pitch - 32;
-        for (int e = tid; e < 5 * nrows * 4; e += nthreads) {
-            const int c = e / (nrows * 4), rem = e - c * (nrows * 4);
-            const int yy = min(ya + (rem >> 2), h - 1), xx = min(x0 + (rem & 3) * 32, xmax);
-            prefetch_l2(R0 + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
+        for (int e = tid; e < NROWS * 4; e += nthreads) {                // 4 lines per row and plane
+            const int yy = min(ya + (e >> 2), h - 1), xx = min(x0 + (e & 3) * 32, xmax);
+            const float* q = R0 + (unsigned)yy * pitch + (unsigned)xx;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) prefetch_l2(q + (size_t)c * plane);
         }
-        for (int e = tid; e < 5 * (nrows + 4) * 6; e += nthreads) {
-            const int c = e / ((nrows + 4) * 6), rem = e - c * ((nrows + 4) * 6);
-            const int yy = min(max(ya - 2 + rem / 6, 0), h - 1), xx = min(max(x0 - 32 + (rem % 6) * 32, 0), xmax);
-            prefetch_l2(R1 + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
+        for (int e = tid; e < (NROWS + 4) * 6; e += nthreads) {
+            const int r = e / 6, l = e - r * 6;
+            const int yy = min(max(ya - 2 + r, 0), h - 1), xx = min(max(x0 - 32 + l * 32, 0), xmax);
+            const float* q = R1 + (unsigned)yy * pitch + (unsigned)xx;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) prefetch_l2(q + (size_t)c * plane);
         }
     }
 }
@@ -136,12 +143,15 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
     // latency per step -- and likewise what phase 3 will read (R0 under the tile, R1 around it), which travels from
     // HBM while phases 1-2 run.
     {
-        const int xlo = max(x0 - C::HALO, 0) & ~(kLine - 1), xhi = min(x0 + kFbTW + C::HALO, w);
-        const int nline = (xhi - xlo + kLine - 1) / kLine, nrow = TH + 2 * MH;
-        for (int e = tid; e < 5 * nrow * nline; e += 256) {
-            const int c = e / (nrow * nline), rem = e - c * (nrow * nline);
-            const int yy = min(max(y0 - MH + rem / nline, 0), h - 1), xx = xlo + (rem % nline) * kLine;
-            prefetch_l2(Mp + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xx);
+        constexpr int NL = (kFbTW + 2 * C::HALO + kLine - 1) / kLine + 1;            // lines per tile row (incl. misalignment)
+        constexpr int NROW = TH + 2 * MH;
+        const int xlo = max(x0 - C::HALO, 0) & ~(kLine - 1), xmaxl = max((w - 1) & ~(kLine - 1), 0);
+        for (int e = tid; e < NROW * NL; e += 256) {
+            const int r = e / NL, l = e - r * NL;
+            const int yy = min(max(y0 - MH + r, 0), h - 1), xx = min(xlo + l * kLine, xmaxl);
+            const MT* q = Mp + (unsigned)yy * pitch + (unsigned)xx;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) prefetch_l2(q + (size_t)c * plane);
         }
     }
     const void* R0 = nullptr;
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
     if (a.Mout) {
         R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
         R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
-        prefetch_r_block<RH>(R0, R1, plane, pitch, w, h, x0, y0, TH, tid, 256);
+        prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, 256);
     }
 
     // ---------------- phase 1: vertical sums ----------------
@@ -221,6 +231,19 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
     if (a.flow || a.Mout) {
         float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
         MT* Mo = a.Mout ? static_cast<MT*>(a.Mout) + (size_t)p * a.m_stride : nullptr;
+        // interior tiles (85 % at 1080p): bounds and the 5-px attenuation ring are decided once per tile
+        const bool inner = (x0 >= 5) && (y0 >= 5) && (x0 + kFbTW <= w - 5) && (y0 + TH <= h - 5);
+        if (inner && Mo && !fo) {
+#pragma unroll 4
+            for (int i = 0; i < 4 * C::RG; ++i) {
+                const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
+                const int x = x0 + cx, y = y0 + r;
+                const float2 f = F[r * kFbTW + cx];
+                float mm[5];
+                update_px_any<RH, false>(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
+                store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, mm);
+            }
+        } else
 #pragma unroll 4
         for (int i = 0; i < 4 * C::RG; ++i) {
             const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
@@ -312,7 +335,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_gauss(const BlurSolveArgs
     if (a.Mout) {
         R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
         R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
-        prefetch_r_block<RH>(R0, R1, plane, pitch, w, h, x0, y0, TH, tid, 256);
+        prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, 256);
     }
 
     // ---------------- phase 1: vertical Gaussian, one scalar column per task ----------------

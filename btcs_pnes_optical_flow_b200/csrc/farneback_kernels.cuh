@@ -311,6 +311,7 @@ __device__ __forceinline__ void unpack_r(const uint4& u, float v[5]) {
 }
 
 // UpdateMatrices for one pixel from packed R (same arithmetic as update_px).  R0/R1 point at pixel (0,0) of the frame.
+template <bool BORDER = true>
 __device__ __forceinline__ void update_px_h(const uint4* __restrict__ R0, const uint4* __restrict__ R1, unsigned pitch,
                                             int w, int h, int x, int y, float dx, float dy, float out[5]) {
     float q[5];
@@ -344,7 +345,7 @@ __device__ __forceinline__ void update_px_h(const uint4* __restrict__ R0, const 
     r3 = (q[1] - r3) * 0.5f;
     r2 += r4 * dy + r6 * dx;
     r3 += r6 * dy + r5 * dx;
-    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+    if (BORDER && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
         const float sc = border_w(x, w) * border_w(y, h);
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
@@ -362,10 +363,11 @@ __device__ __forceinline__ int ring_slot(int slot0, int p, int nslots) {
 }
 
 // Layout-agnostic front end: RH = packed fp16 (slot_stride counts uint4 pixels), else fp32 planes (slot_stride in floats).
-template <bool RH>
+// BORDER = false: the caller guarantees the pixel lies outside the 5-px attenuation ring (interior tiles).
+template <bool RH, bool BORDER = true>
 __device__ __forceinline__ void update_px_any(const void* R0, const void* R1, unsigned plane, unsigned pitch, int w, int h,
                                               int x, int y, float dx, float dy, float out[5]) {
-    if (RH) update_px_h(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), pitch, w, h, x, y, dx, dy, out);
+    if (RH) update_px_h<BORDER>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), pitch, w, h, x, y, dx, dy, out);
     else update_px(static_cast<const float*>(R0), static_cast<const float*>(R1), plane, pitch, w, h, x, y, dx, dy, out);
 }
 

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(MarchCfg<MH>::NT, 1) k_flow_iter_box(const Mar
             const int buf = blk & 1;
             const int ybase = ya + blk * C::RB;
             // pull what this block's tail will gather into L2 while the horizontal pass runs
-            if (Mo) prefetch_r_block<RH>(R0, R1, plane, pitch, w, h, x0, ybase, C::RB, ctid, C::NCMP);
+            if (Mo) prefetch_r_block<RH, C::RB>(R0, R1, plane, pitch, w, h, x0, ybase, ctid, C::NCMP);
             named_bar_sync(buf ? BAR_FULL1 : BAR_FULL0, C::NT);
             // ---- horizontal sums + solve: GPT groups of 4 pixels per thread ----
             float2 fl[C::GPT][4];
