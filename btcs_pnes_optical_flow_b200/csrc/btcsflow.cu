@@ -293,7 +293,7 @@ int launch_polyexp(const float* I, int pitch, size_t frame_stride, int w, int h,
 
 int launch_update(const bf::UpdateArgs& a, int np, bool r_half, cudaStream_t st) {
     dim3 b(64, 4);
-    dim3 g(cdiv(a.w, 64), cdiv(a.h, 4), np);
+    dim3 g(cdiv(a.w, 64), cdiv(a.h, 4 * bf::kUpdRows), np);
     if (r_half) bf::k_update<true><<<g, b, 0, st>>>(a);
     else bf::k_update<false><<<g, b, 0, st>>>(a);
     LAUNCH_CHECK();

@@ -410,25 +410,62 @@ struct UpdateArgs {
     float2* flow_out; int flow_out_pitch; size_t flow_out_stride;          // optional: write flow_init
 };
 
+// Each thread handles kUpdRows rows of one column: the x-side resize table entry, the ring-slot pointers and the kernel
+// parameters are fetched once per thread instead of once per pixel (the per-pixel version was ~330 SASS instructions, a
+// third of them index arithmetic and constant loads; ncu, profiles/).
+constexpr int kUpdRows = 4;
+
 template <bool RH>
 __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int yb = (blockIdx.y * blockDim.y + threadIdx.y) * kUpdRows;
     const int p = blockIdx.z;
-    if (x >= a.w || y >= a.h) return;
-    float2 fl = make_float2(0.f, 0.f);
-    if (a.flow_mode == 1) fl = a.flow[(size_t)p * a.flow_stride + (unsigned)y * (unsigned)a.flow_pitch + (unsigned)x];
-    else if (a.flow_mode == 2)
-        fl = upsample_flow_px(a.flow + (size_t)p * a.flow_stride, a.flow_pitch, a.ws, a.hs, a.tab, x, y, a.mult);
-    if (a.flow_out) a.flow_out[(size_t)p * a.flow_out_stride + (unsigned)y * (unsigned)a.flow_out_pitch + (unsigned)x] = fl;
-    if (!a.M) return;
-    const void* R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
-    const void* R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
-    float m[5];
-    update_px_any<RH>(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, a.w, a.h, x, y, fl.x, fl.y, m);
+    if (x >= a.w || yb >= a.h) return;
     using MT = typename MStore<RH>::type;
-    store_m(static_cast<MT*>(a.M) + (size_t)p * a.m_stride, (unsigned)a.plane_stride,
-            (unsigned)y * (unsigned)a.pitch + (unsigned)x, m);
+    const int w = a.w, h = a.h;
+    const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
+    const void* R0 = nullptr;
+    const void* R1 = nullptr;
+    MT* Mo = nullptr;
+    if (a.M) {
+        R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
+        R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
+        Mo = static_cast<MT*>(a.M) + (size_t)p * a.m_stride;
+    }
+    const float2* fin = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
+    float2* fout = a.flow_out ? a.flow_out + (size_t)p * a.flow_out_stride : nullptr;
+    int ux0 = 0, ux1 = 0;
+    float ua = 0.f;
+    if (a.flow_mode == 2) { ux0 = a.tab.ix[x]; ua = a.tab.ax[x]; ux1 = min(ux0 + 1, a.ws - 1); }
+    // a block of rows away from the 5-px ring needs no attenuation test (block-uniform)
+    const bool inner = (x >= 5) && (x < w - 5) && (yb >= 5) && (yb + kUpdRows <= h - 5);
+#pragma unroll
+    for (int k = 0; k < kUpdRows; ++k) {
+        const int y = yb + k;
+        if (y >= h) break;
+        float2 fl = make_float2(0.f, 0.f);
+        if (a.flow_mode == 1) {
+            fl = fin[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x];
+        } else if (a.flow_mode == 2) {
+            // bilinear sample of the coarser flow (cv2.resize INTER_LINEAR) times mult
+            const int y0 = a.tab.iy[y], y1 = min(y0 + 1, a.hs - 1);
+            const float b = a.tab.ay[y];
+            const unsigned r0 = (unsigned)y0 * (unsigned)a.flow_pitch, r1 = (unsigned)y1 * (unsigned)a.flow_pitch;
+            const float2 p00 = fin[r0 + (unsigned)ux0], p01 = fin[r0 + (unsigned)ux1];
+            const float2 p10 = fin[r1 + (unsigned)ux0], p11 = fin[r1 + (unsigned)ux1];
+            const float h0x = p00.x * (1.f - ua) + p01.x * ua, h0y = p00.y * (1.f - ua) + p01.y * ua;
+            const float h1x = p10.x * (1.f - ua) + p11.x * ua, h1y = p10.y * (1.f - ua) + p11.y * ua;
+            fl.x = (h0x * (1.f - b) + h1x * b) * a.mult;
+            fl.y = (h0y * (1.f - b) + h1y * b) * a.mult;
+        }
+        if (fout) fout[(unsigned)y * (unsigned)a.flow_out_pitch + (unsigned)x] = fl;
+        if (Mo) {
+            float m[5];
+            if (inner) update_px_any<RH, false>(R0, R1, plane, pitch, w, h, x, y, fl.x, fl.y, m);
+            else update_px_any<RH, true>(R0, R1, plane, pitch, w, h, x, y, fl.x, fl.y, m);
+            store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, m);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
