@@ -529,41 +529,13 @@ struct FastPeCfg {
     static constexpr size_t SMEM = (size_t)3 * kFbTH * VP * sizeof(float);
 };
 
+// Horizontal pass of the polynomial expansion from the shared vertical-pass result + the 5-coefficient store.
 template <int N, bool RH>
-__global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I, int pitch, size_t frame_stride, int w,
-                                                    int h, void* __restrict__ Rv, size_t plane_stride,
-                                                    size_t slot_stride, int slot0, int nslots, const PolyCoef pc) {
+__device__ __forceinline__ void polyexp_horizontal_store(const float* smem, int x0, int y0, int f, int pitch, int w, int h,
+                                                         void* __restrict__ Rv, size_t plane_stride, size_t slot_stride,
+                                                         int slot0, int nslots, const PolyCoef& pc) {
     using C = FastPeCfg<N>;
-    extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kFbTH, f = blockIdx.z;
-    const float* img = I + (size_t)f * frame_stride;
-    for (int task = tid; task < C::RG * C::NCOL; task += 256) {
-        const int rg = task / C::NCOL, col = task - rg * C::NCOL;
-        const int gx = min(max(x0 - C::HALO + col, 0), w - 1);
-        const int yb = y0 + rg * C::RPG - N;
-        float v[C::RPG + 2 * N];
-#pragma unroll
-        for (int i = 0; i < C::RPG + 2 * N; ++i) v[i] = __ldg(img + (size_t)min(max(yb + i, 0), h - 1) * pitch + gx);
-        float* dst = smem + (rg * C::RPG) * C::VP + col;
-#pragma unroll
-        for (int j = 0; j < C::RPG; ++j) {
-            const float c = v[j + N];
-            float t0 = c * pc.g[0], t1 = 0.f, t2 = 0.f;
-#pragma unroll
-            for (int k = 1; k <= N; ++k) {
-                const float up = v[j + N - k], dn = v[j + N + k];
-                const float pp = up + dn;
-                t0 = fmaf(pc.g[k], pp, t0);
-                t1 = fmaf(pc.xg[k], dn - up, t1);
-                t2 = fmaf(pc.xxg[k], pp, t2);
-            }
-            dst[j * C::VP] = t0;
-            dst[(kFbTH + j) * C::VP] = t1;
-            dst[(2 * kFbTH + j) * C::VP] = t2;
-        }
-    }
-    __syncthreads();
     const int g = tid & 31, rb = tid >> 5;
     const int slot = (slot0 + f) % nslots;
     float* Rb = RH ? nullptr : static_cast<float*>(Rv) + (size_t)slot * slot_stride;
@@ -631,6 +603,44 @@ __global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I,
     }
 }
 
+template <int N, bool RH>
+__global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I, int pitch, size_t frame_stride, int w,
+                                                    int h, void* __restrict__ Rv, size_t plane_stride,
+                                                    size_t slot_stride, int slot0, int nslots, const PolyCoef pc) {
+    using C = FastPeCfg<N>;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kFbTH, f = blockIdx.z;
+    const float* img = I + (size_t)f * frame_stride;
+    for (int task = tid; task < C::RG * C::NCOL; task += 256) {
+        const int rg = task / C::NCOL, col = task - rg * C::NCOL;
+        const int gx = min(max(x0 - C::HALO + col, 0), w - 1);
+        const int yb = y0 + rg * C::RPG - N;
+        float v[C::RPG + 2 * N];
+#pragma unroll
+        for (int i = 0; i < C::RPG + 2 * N; ++i) v[i] = __ldg(img + (size_t)min(max(yb + i, 0), h - 1) * pitch + gx);
+        float* dst = smem + (rg * C::RPG) * C::VP + col;
+#pragma unroll
+        for (int j = 0; j < C::RPG; ++j) {
+            const float c = v[j + N];
+            float t0 = c * pc.g[0], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float up = v[j + N - k], dn = v[j + N + k];
+                const float pp = up + dn;
+                t0 = fmaf(pc.g[k], pp, t0);
+                t1 = fmaf(pc.xg[k], dn - up, t1);
+                t2 = fmaf(pc.xxg[k], pp, t2);
+            }
+            dst[j * C::VP] = t0;
+            dst[(kFbTH + j) * C::VP] = t1;
+            dst[(2 * kFbTH + j) * C::VP] = t2;
+        }
+    }
+    __syncthreads();
+    polyexp_horizontal_store<N, RH>(smem, x0, y0, f, pitch, w, h, Rv, plane_stride, slot_stride, slot0, nslots, pc);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Pyramid.  Every level is made from the FULL-RESOLUTION frame: GaussianBlur(REFLECT_101) then bilinear
 // resize.  Scale 1.0 (level k = 0) always uses the fixed [1 2 1]/4 taps and no resize: k_level0_blur does that 3x3
@@ -671,6 +681,84 @@ __global__ void __launch_bounds__(256) k_level0_blur(const T* __restrict__ src, 
             if (x < W) orow[x] = hr[0] * 0.25f + hr[1] * 0.5f + hr[2] * 0.25f;
         }
     }
+}
+
+// k_polyexp_l0<N, RH, T>: pyramid level 0 and its polynomial expansion in one kernel.  The uint8 (or float) frame tile
+// goes to shared memory, the exact 3x3 [1 2 1]/4 REFLECT_101 blur (scale 1) is evaluated into a second shared
+// tile at REPLICATE-clamped coordinates (what the expansion's borders need), and the two separable passes of
+// k_polyexp run from there.  Saves the level-0 image round trip through HBM (4 B/px written + read) and one launch.
+template <int N>
+struct FusedPeCfg {
+    using P = FastPeCfg<N>;
+    static constexpr int BROWS = kFbTH + 2 * N;                 // blurred tile rows
+    static constexpr int BP = P::NCOL + 4;                      // blurred tile pitch
+    static constexpr int UROWS = BROWS + 2, UP = P::NCOL + 2 + 2;   // raw tile (one more ring for the 3x3 blur)
+    static constexpr int T_FLOATS = 3 * kFbTH * P::VP;          // vertical-pass result; the raw tile aliases it
+    static constexpr size_t SMEM = (size_t)(T_FLOATS + BROWS * BP) * sizeof(float);
+    static_assert(UROWS * UP <= T_FLOATS, "raw tile must fit in the aliased region");
+};
+
+template <int N, bool RH, typename T>
+__global__ void __launch_bounds__(256, 2) k_polyexp_l0(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes,
+                                                       int pitch, int w, int h, void* __restrict__ Rv, size_t plane_stride,
+                                                       size_t slot_stride, int slot0, int nslots, const PolyCoef pc) {
+    using C = FastPeCfg<N>;
+    using Fz = FusedPeCfg<N>;
+    extern __shared__ __align__(16) float smem[];
+    float* tbuf = smem;                                   // [3][TH][VP]   (raw tile U[UROWS][UP] lives here first)
+    float* U = smem;
+    float* Bt = smem + Fz::T_FLOATS;                      // [BROWS][BP]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kFbTH, f = blockIdx.z;
+    const char* base = (const char*)src + (size_t)f * src_frame_bytes;
+    // raw tile: U[uy][ux] = frame[reflect101(y0 - N - 1 + uy)][reflect101(x0 - HALO - 1 + ux)] (coordinates limited to
+    // [-1, size] first: anything further out is never used by an in-image blurred sample)
+    for (int e = tid; e < Fz::UROWS * (C::NCOL + 2); e += 256) {
+        const int uy = e / (C::NCOL + 2), ux = e - uy * (C::NCOL + 2);
+        const int gy = reflect101(min(max(y0 - N - 1 + uy, -1), h), h), gx = reflect101(min(max(x0 - C::HALO - 1 + ux, -1), w), w);
+        U[uy * Fz::UP + ux] = load_px((const T*)(base + (size_t)gy * src_pitch_bytes) + gx);
+    }
+    __syncthreads();
+    // blurred tile at replicate-clamped coordinates: tile index ranges that fall inside the image
+    const int ty_lo = max(0, N - y0), ty_hi = min(Fz::BROWS - 1, (h - 1) - (y0 - N));
+    const int tx_lo = max(0, C::HALO - x0), tx_hi = min(C::NCOL - 1, (w - 1) - (x0 - C::HALO));
+    for (int e = tid; e < Fz::BROWS * C::NCOL; e += 256) {
+        const int ty = e / C::NCOL, tx = e - ty * C::NCOL;
+        const int tyc = min(max(ty, ty_lo), ty_hi), txc = min(max(tx, tx_lo), tx_hi);
+        const float* q = U + tyc * Fz::UP + txc;                               // top-left of the 3x3 neighbourhood
+        float hr[3];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) hr[dy] = q[dy * Fz::UP] * 0.25f + q[dy * Fz::UP + 1] * 0.5f + q[dy * Fz::UP + 2] * 0.25f;
+        Bt[ty * Fz::BP + tx] = hr[0] * 0.25f + hr[1] * 0.5f + hr[2] * 0.25f;   // row filter first, like cv2
+    }
+    __syncthreads();
+    // vertical pass from the blurred tile (already border-replicated)
+    for (int task = tid; task < C::RG * C::NCOL; task += 256) {
+        const int rg = task / C::NCOL, col = task - rg * C::NCOL;
+        const float* bsrc = Bt + (rg * C::RPG) * Fz::BP + col;
+        float v[C::RPG + 2 * N];
+#pragma unroll
+        for (int i = 0; i < C::RPG + 2 * N; ++i) v[i] = bsrc[i * Fz::BP];
+        float* dst = tbuf + (rg * C::RPG) * C::VP + col;
+#pragma unroll
+        for (int j = 0; j < C::RPG; ++j) {
+            const float c = v[j + N];
+            float t0 = c * pc.g[0], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float up = v[j + N - k], dn = v[j + N + k];
+                const float pp = up + dn;
+                t0 = fmaf(pc.g[k], pp, t0);
+                t1 = fmaf(pc.xg[k], dn - up, t1);
+                t2 = fmaf(pc.xxg[k], pp, t2);
+            }
+            dst[j * C::VP] = t0;
+            dst[(kFbTH + j) * C::VP] = t1;
+            dst[(2 * kFbTH + j) * C::VP] = t2;
+        }
+    }
+    __syncthreads();
+    polyexp_horizontal_store<N, RH>(tbuf, x0, y0, f, pitch, w, h, Rv, plane_stride, slot_stride, slot0, nslots, pc);
 }
 
 struct PyrLevelDesc {
@@ -774,6 +862,22 @@ inline void launch_polyexp_fast_n(const float* I, int pitch, size_t frame_stride
     cudaFuncSetAttribute(k_polyexp<N, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     dim3 g((w + kFbTW - 1) / kFbTW, (h + kFbTH - 1) / kFbTH, nf);
     k_polyexp<N, RH><<<g, 256, C::SMEM, st>>>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, pc);
+}
+
+template <typename T>
+inline void launch_polyexp_l0(const T* src, size_t src_pitch_bytes, size_t src_frame_bytes, int pitch, int w, int h, void* R,
+                              size_t plane_stride, size_t slot_stride, int slot0, int nslots, int nf, const PolyCoef& pc,
+                              bool r_half, cudaStream_t st) {
+    dim3 g((w + kFbTW - 1) / kFbTW, (h + kFbTH - 1) / kFbTH, nf);
+#define BF_LAUNCH_L0(NN, RHH)                                                                                             \
+    do {                                                                                                                  \
+        cudaFuncSetAttribute(k_polyexp_l0<NN, RHH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPeCfg<NN>::SMEM); \
+        k_polyexp_l0<NN, RHH, T><<<g, 256, FusedPeCfg<NN>::SMEM, st>>>(src, src_pitch_bytes, src_frame_bytes, pitch, w, h, R,    \
+                                                                       plane_stride, slot_stride, slot0, nslots, pc);      \
+    } while (0)
+    if (pc.n == 5) { if (r_half) BF_LAUNCH_L0(5, true); else BF_LAUNCH_L0(5, false); }
+    else { if (r_half) BF_LAUNCH_L0(7, true); else BF_LAUNCH_L0(7, false); }
+#undef BF_LAUNCH_L0
 }
 
 inline void launch_polyexp_fast(const float* I, int pitch, size_t frame_stride, int w, int h, void* R,

@@ -138,6 +138,7 @@ def test_all_kernel_variants_agree(monkeypatch):
             for name, env in (("tile", {}), ("march", {"BTCSFLOW_KERNEL": "march"}),
                               ("tile_f32", {"BTCSFLOW_R_STORAGE": "f32"}),
                               ("march_f32", {"BTCSFLOW_KERNEL": "march", "BTCSFLOW_R_STORAGE": "f32"}),
+                              ("fused_l0", {"BTCSFLOW_FUSED_L0": "1"}),
                               ("generic", {"BTCSFLOW_NO_FAST": "1"})):
                 for k, v in env.items():
                     monkeypatch.setenv(k, v)
@@ -150,6 +151,7 @@ def test_all_kernel_variants_agree(monkeypatch):
             assert epe(outs["march_f32"], outs["generic"])[1] < 1e-4 and epe(outs["tile_f32"], outs["generic"])[1] < 1e-4
             # compact storage (fp16 R and M): both kernels quantise the same values, summation order differs
             assert epe(outs["march"], outs["generic"])[1] < 2e-3 and epe(outs["tile"], outs["march"])[1] < 1e-3
+            assert epe(outs["fused_l0"], outs["tile"])[1] < 1e-3        # level-0 blur fused into the expansion (opt-in)
 
 
 def test_1080p_full_size_properties():
