@@ -155,8 +155,12 @@ def run_reference(args, spec, params):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(spec, params, pairs_per_step, batch):
-    return {"workload": f"C2: synthetic {spec.W}x{spec.H} {spec.fps:g} fps VEEG-like clip (decaying 3 Hz chirp patch), "
+def workload_config(spec, params, pairs_per_step, batch, storage_bits=None):
+    return {"storage": None if storage_bits is None else
+            (f"polynomial coefficients and update matrices stored as fp{storage_bits} "
+             f"({'compact plan, storage only: all arithmetic fp32' if storage_bits == 16 else 'exact plan'}); "
+             "parity gates asserted in tests/test_gpu_flow.py"),
+            "workload": f"C2: synthetic {spec.W}x{spec.H} {spec.fps:g} fps VEEG-like clip (decaying 3 Hz chirp patch), "
                         f"full-frame ROI, cv2 default Farneback params, flow->ROI series->band-pass->PC1",
             "width": spec.W, "height": spec.H, "fb_params": params, "pairs_per_step_per_gpu": pairs_per_step,
             "pairs_per_launch": batch, "pca": {"win_sec": 2.0, "step_sec": 0.1, "fs": spec.fps},
@@ -298,18 +302,39 @@ def run_ours(args, spec, params):
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
                    "sample": f"{n_cpu} consecutive 1080p pairs of the same clip, 1 pass ({ms_cpu / 1e3:.1f} s); cv2 {ver} "
                              f"calcOpticalFlowFarneback + numpy ROI reduction, ThreadPool({threads}) x cv2.setNumThreads(1)"}
+        exact = None
+        if world == 1 and not args.no_exact:
+            # transparency: the same device-resident step on an exact (all-fp32 storage) plan
+            plan_x = B.FlowPlan(spec.W, spec.H, params, max_pairs=min(args.max_pairs, 16), max_rois=1, device=local_rank,
+                                exact=True)
+            def step_exact():
+                series = plan_x.flow_series(frames_dev, None, None, mask_dev)
+                return finish(D.gather_series(series[:, 1:], rows, T_total))
+            for _ in range(2):
+                step_exact()
+            torch.cuda.synchronize()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            for _ in range(2):
+                step_exact()
+            x1.record()
+            torch.cuda.synchronize()
+            exact = {"value": P * 2 / (x0.elapsed_time(x1) / 1e3), "unit": UNIT, "storage": "fp32 planes (exact plan)",
+                     "steps": 2}
+            plan_x.close()
         n_roi = 1
         h2d = frames_host.nbytes + mask_host.size + 2 * (P + 1) * 2 * 8 + (2 * T_total * 8 if rank == 0 else 0)
         d2h = n_roi * (P + 1) * 3 * 4 + T_total * 8
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(spec, params, P, args.max_pairs),
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(spec, params, P, args.max_pairs, plan.coeff_storage_bits),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "workspace_bytes": plan.workspace_bytes,
+            "workspace_bytes": plan.workspace_bytes, "exact_f32_storage": exact,
         }
         print(json.dumps(line), flush=True)
     plan.close()
@@ -325,6 +350,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=256, help="frame pairs per GPU per step")
     ap.add_argument("--max-pairs", type=int, default=64, help="frame pairs per batched kernel launch")
+    ap.add_argument("--no-exact", action="store_true", help="skip the secondary measurement on an exact (fp32 storage) plan")
     args = ap.parse_args()
     from btcs_pnes_optical_flow_b200 import synthetic as syn
     spec, params = syn.config_spec("C2")
