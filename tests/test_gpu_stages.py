@@ -96,3 +96,27 @@ def test_upsample_flow(T):
         ref = fb.resize_bilinear(f, w, h) * np.float32(2.0)
         got = stages.upsample_flow(_dev(T, f), w, h, 2.0).cpu().numpy()
         assert np.abs(got - ref).max() < 1e-5
+
+
+def test_no_out_of_bounds_writes(T):
+    """Every stage kernel on awkward sizes (ragged tiles, odd widths) with canary bands around the outputs."""
+    import btcs_pnes_optical_flow_b200 as B
+    from btcs_pnes_optical_flow_b200 import stages
+    rng = np.random.default_rng(3)
+    stages.check_guards()
+    for (h, w) in ((24, 128), (25, 132), (83, 120), (97, 131), (50, 300), (33, 36)):
+        img = rng.random((h, w)).astype(np.float32) * 255
+        for n in (5, 7, 3):
+            stages.poly_exp(_dev(T, img), n, 1.2)
+        R = rng.standard_normal((5, h, w)).astype(np.float32)
+        fl = (rng.standard_normal((h, w, 2)) * 4).astype(np.float32)
+        M = stages.update_matrices(_dev(T, R), _dev(T, R[::-1].copy()), _dev(T, fl))
+        for ws, flags in ((15, 0), (21, 256), (9, 0), (16, 256)):
+            stages.blur_solve(M, ws, flags)
+        stages.upsample_flow(_dev(T, fl), 2 * w + 1, 2 * h - 1, 2.0)
+        if min(h, w) >= 32:
+            plan = B.FlowPlan(w, h, dict(B.FB_PARAMS, levels=2))
+            for i in range(len(plan.scales())):
+                stages.level_image(plan, _dev(T, img.astype(np.uint8)), i)
+            plan.close()
+    assert stages.check_guards() > 50
