@@ -858,10 +858,12 @@ int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* 
         LAUNCH_CHECK();
         roi.masks = p->d_masks; roi.n_roi = n_roi; roi.ex = p->d_ex; roi.ey = p->d_ey; roi.out = p->d_out; roi.T = T;
     }
-    // the copy stream must not overwrite a staging buffer a previous call on `st` may still be reading
+    // Chunks of up to B pairs, double-buffered: chunk c+1 travels on the copy stream while chunk c computes.  The first
+    // chunk is kept short so that compute starts after ~8 frames have arrived instead of after a full B+1-frame chunk.
     int chunk = 0;
-    for (int t0 = 0; t0 < T - 1; t0 += p->B, ++chunk) {
-        const int np = std::min(p->B, T - 1 - t0);
+    for (int t0 = 0; t0 < T - 1; ++chunk) {
+        const int cap = (chunk == 0) ? std::min(p->B, 8) : p->B;
+        const int np = std::min(cap, T - 1 - t0);
         const int tf = (t0 == 0) ? 0 : t0 + 1;
         const int nf = t0 + np - tf + 1;
         const int b = chunk & 1;
@@ -877,6 +879,7 @@ int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* 
         if (flow_out)
             CU(cudaMemcpyAsync(flow_out + (size_t)t0 * fb * 2, p->stage_flow, (size_t)np * fb * 2 * sizeof(float),
                                cudaMemcpyDeviceToHost, st));
+        t0 += np;
     }
     if (n_roi > 0)
         CU(cudaMemcpyAsync(out, p->d_out, (size_t)n_roi * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
