@@ -6,7 +6,7 @@ hand-written sm_100a CUDA behind a C-ABI (include/btcsflow.h, libbtcsflow.so).  
 host (metrics.py, mirrors optical_PC1.py).
 """
 from .flow import (FB_PARAMS, FlowPlan, BtcsFlowError, Cv2CompatError, OPTFLOW_FARNEBACK_GAUSSIAN,
-                   OPTFLOW_USE_INITIAL_FLOW, build_roi_mask, calcOpticalFlowFarneback, clear_plans,
+                   OPTFLOW_USE_INITIAL_FLOW, bgr_to_gray, build_roi_mask, calcOpticalFlowFarneback, clear_plans,
                    compute_roi_mean_body_flow, get_plan, run_body_axis_flow_core, skel_index_from_time)
 from .pca import (bandpass_nanrobust, bandpass_nanrobust_device, butter_bandpass_sos, dynamic_pc1_sliding, flow_to_pc1,
                   pc1_sliding_batched)

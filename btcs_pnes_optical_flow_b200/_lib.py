@@ -61,6 +61,7 @@ _SIGNATURES = {
     "bf_pc1_sliding": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _vp]),
     "bf_pc1_sliding_batched": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp]),
     "bf_pc1_sliding_host": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _i, _vp]),
+    "bf_bgr2gray": (_i, [_vp, _i, _i, _i, _sz, _vp, _sz, _vp]),
     "bf_bandpass_nanrobust": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "bf_sosfilt_zi": (_i, [_vp, _i, _vp]),
     "bf_stage_level_image": (_i, [_vp, _vp, _i, _sz, _i, _vp, _vp]),

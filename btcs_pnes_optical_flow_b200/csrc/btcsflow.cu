@@ -974,6 +974,20 @@ int bf_pc1_sliding_host(const double* vx, const double* vy, int n, int win_n, in
     return rc;
 }
 
+// ---- BGR -> gray -----------------------------------------------------------------------------------------
+
+int bf_bgr2gray(const uint8_t* bgr, int n_frames, int width, int height, size_t in_pitch_bytes, uint8_t* gray,
+                size_t out_pitch_bytes, void* stream) {
+    if (!bgr || !gray || n_frames < 0 || width <= 0 || height <= 0) return fail(BF_E_INVALID, "bad arguments");
+    if (in_pitch_bytes < (size_t)width * 3 || out_pitch_bytes < (size_t)width) return fail(BF_E_INVALID, "pitch smaller than a row");
+    if (n_frames == 0) return 0;
+    dim3 g(cdiv(cdiv(width, 4), 256), height, n_frames);
+    bf::k_bgr2gray<<<g, 256, 0, (cudaStream_t)stream>>>(bgr, in_pitch_bytes, in_pitch_bytes * height, width, height, gray,
+                                                        out_pitch_bytes, out_pitch_bytes * height);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 // ---- band-pass -------------------------------------------------------------------------------------------
 
 int bf_sosfilt_zi(const double* sos, int n_sections, double* zi) {

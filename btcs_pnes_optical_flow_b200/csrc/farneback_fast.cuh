@@ -765,6 +765,33 @@ __global__ void __launch_bounds__(256, 2) k_polyexp_l0(const T* __restrict__ src
     polyexp_horizontal_store<N, RH>(tbuf, x0, y0, f, pitch, w, h, Rv, plane_stride, slot_stride, slot0, nslots, pc);
 }
 
+// BGR -> gray exactly like cv2.cvtColor(COLOR_BGR2GRAY) on uint8 (/root/reference/optical_flow.py:227; SURVEY section 8 row
+// f-2): 15-bit fixed point, gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15 (matches cv2 4.13 on every (b, g, r) of a
+// 5-step grid and 262144 random triples, tests/test_host_logic.py).  4 pixels per thread: 3 x 32-bit loads, 1 store.
+__global__ void __launch_bounds__(256) k_bgr2gray(const uint8_t* __restrict__ bgr, size_t in_pitch_bytes, size_t in_frame_bytes,
+                                                  int W, int H, uint8_t* __restrict__ gray, size_t out_pitch_bytes,
+                                                  size_t out_frame_bytes) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, f = blockIdx.z;
+    if (x4 >= W || y >= H) return;
+    const uint8_t* in = bgr + (size_t)f * in_frame_bytes + (size_t)y * in_pitch_bytes + (size_t)x4 * 3;
+    uint8_t* out = gray + (size_t)f * out_frame_bytes + (size_t)y * out_pitch_bytes + x4;
+    auto conv = [](unsigned b, unsigned g, unsigned r) { return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15; };
+    const bool vec = (x4 + 3 < W) && ((reinterpret_cast<uintptr_t>(in) & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
+    if (vec) {
+        const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(in)), w1 = __ldg(reinterpret_cast<const unsigned*>(in) + 1),
+                       w2 = __ldg(reinterpret_cast<const unsigned*>(in) + 2);
+        // bytes: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+        const unsigned p0 = conv(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+        const unsigned p1 = conv(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+        const unsigned p2 = conv((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+        const unsigned p3 = conv((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+        *reinterpret_cast<unsigned*>(out) = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    } else {
+        for (int j = 0; j < 4 && x4 + j < W; ++j) out[j] = (uint8_t)conv(in[3 * j], in[3 * j + 1], in[3 * j + 2]);
+    }
+}
+
 struct PyrLevelDesc {
     const int* ix; const float* ax; const float* kern;
     float* tmp; size_t tmp_frame_stride;

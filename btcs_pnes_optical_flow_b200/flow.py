@@ -369,6 +369,27 @@ def build_roi_mask(H: int, W: int, roi_polygon_xy: np.ndarray) -> np.ndarray:
     return mask.astype(bool)
 
 
+def bgr_to_gray(frames_bgr):
+    """cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) (optical_flow.py:227) on the GPU, bit-exact for uint8.
+
+    frames_bgr: uint8 [T, H, W, 3] or [H, W, 3]; numpy (returns numpy) or a torch CUDA tensor (stays on the device)."""
+    import torch
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise BtcsFlowError(_lib.BF_E_NODEVICE, "no CUDA device: bgr_to_gray has no CPU fallback")
+    is_torch = _is_torch(frames_bgr)
+    x = frames_bgr if is_torch else torch.from_numpy(np.ascontiguousarray(frames_bgr)).cuda()
+    if x.dtype != torch.uint8 or x.shape[-1] != 3 or x.dim() not in (3, 4):
+        raise Cv2CompatError(-1, "frames must be uint8 [T, H, W, 3] or [H, W, 3]")
+    one = x.dim() == 3
+    x = (x[None] if one else x).contiguous()
+    T, H, W, _ = x.shape
+    out = torch.empty((T, H, W), dtype=torch.uint8, device=x.device)
+    check(lib.bf_bgr2gray(x.data_ptr(), T, W, H, W * 3, out.data_ptr(), W, _current_stream_ptr(x.device.index)))
+    out = out[0] if one else out
+    return out if is_torch else out.cpu().numpy()
+
+
 def skel_index_from_time(t_sec: float, time_all: np.ndarray) -> int:
     """Largest upstream index with time_all[idx] <= t_sec, clipped (optical_flow.py:122-133)."""
     idx = int(np.searchsorted(time_all, t_sec, side="right")) - 1
@@ -398,12 +419,13 @@ def compute_roi_mean_body_flow(prev_gray, gray, ex, ey, roi_mask, fb_params: dic
 
 
 def run_body_axis_flow_core(video_path: str, inter_npz: str, roi_polygon_xy: np.ndarray, out_csv: str,
-                            chunk_frames: int = 64, fb_params: dict | None = None) -> None:
+                            chunk_frames: int = 64, fb_params: dict | None = None, gray_on_device: bool = True) -> None:
     """Video -> flow.csv with the reference's columns and NaN rules (optical_flow.py:195-259).
 
-    Decode and BGR->gray stay on the host (cv2.VideoCapture / cvtColor: out of scope, SURVEY section 2 row 5);
-    frames are handed to the GPU in chunks that overlap by one frame, so every row is still the pair
-    (frame-1, frame) and `prev` advances even across rows whose axes are invalid (optical_flow.py:249)."""
+    Decode stays on the host (cv2.VideoCapture: out of scope); BGR->gray runs on the GPU
+    (bit-exact with cv2.cvtColor; gray_on_device=False keeps it on the host like the reference).  Frames are handed
+    to the GPU in chunks that overlap by one frame, so every row is still the pair (frame-1, frame) and `prev`
+    advances even across rows whose axes are invalid (optical_flow.py:249)."""
     import cv2
     import pandas as pd
 
@@ -438,7 +460,7 @@ def run_body_axis_flow_core(video_path: str, inter_npz: str, roi_polygon_xy: np.
                 if not ret:
                     done = True
                     break
-                grays.append(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY))
+                grays.append(frame if gray_on_device else cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY))
                 t_msec = cap.get(cv2.CAP_PROP_POS_MSEC)
                 t_sec = float(t_msec) / 1000.0 if (t_msec is not None and t_msec > 0) else frame_idx / fps
                 sk = skel_index_from_time(t_sec, time_all)
@@ -446,14 +468,22 @@ def run_body_axis_flow_core(video_path: str, inter_npz: str, roi_polygon_xy: np.
                 frame_idx += 1
             if not grays:
                 break
-            stack = grays if carry is None else [carry] + grays
+            stack = grays if (carry is None or gray_on_device) else [carry] + grays
             off = 0 if carry is None else 1
+            n_stack = len(grays) + off
             idx = [m[2] for m in meta]
-            ex = np.full((len(stack), 2), np.nan)
-            ey = np.full((len(stack), 2), np.nan)
+            ex = np.full((n_stack, 2), np.nan)
+            ey = np.full((n_stack, 2), np.nan)
             ex[off:] = ex_all[idx]
             ey[off:] = ey_all[idx]
-            series = plan.flow_series(np.stack(stack), ex, ey, roi_mask)[0]
+            if gray_on_device:
+                import torch
+                new_gray = bgr_to_gray(torch.from_numpy(np.stack(grays)).cuda())        # [n, H, W] uint8 on the device
+                dev_stack = new_gray if carry is None else torch.cat([carry[None], new_gray])
+                series = plan.flow_series(dev_stack, ex, ey, roi_mask)[0].cpu().numpy()
+                grays = [new_gray[-1]]                                                  # device tensor carried over
+            else:
+                series = plan.flow_series(np.stack(stack), ex, ey, roi_mask)[0]
             for j, (fi, t_sec, sk) in enumerate(meta):
                 ok = bool(np.isfinite(ex_all[sk]).all() and np.isfinite(ey_all[sk]).all())
                 vx, vy, mag = (float(v) for v in series[off + j])
@@ -469,6 +499,6 @@ def run_body_axis_flow_core(video_path: str, inter_npz: str, roi_polygon_xy: np.
 
 __all__ = [
     "FB_PARAMS", "FlowPlan", "get_plan", "clear_plans", "calcOpticalFlowFarneback", "build_roi_mask",
-    "skel_index_from_time", "compute_roi_mean_body_flow", "run_body_axis_flow_core",
+    "skel_index_from_time", "compute_roi_mean_body_flow", "run_body_axis_flow_core", "bgr_to_gray",
     "OPTFLOW_FARNEBACK_GAUSSIAN", "OPTFLOW_USE_INITIAL_FLOW", "BtcsFlowError", "Cv2CompatError",
 ]

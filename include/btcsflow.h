@@ -134,6 +134,13 @@ int bf_pc1_sliding_batched(const double* vx, const double* vy, int n_series, int
 int bf_pc1_sliding_host(const double* vx, const double* vy, int n, int win_n, int step_n, double ref_x,
                         double ref_y, int min_samples, double* pc1_out);
 
+/* ---- BGR -> gray (replaces cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY), optical_flow.py:227) ---------------- */
+
+/* bgr: uint8 [n_frames, H, in_pitch_bytes] interleaved B,G,R (cv2.VideoCapture layout); gray: uint8 [n_frames, H,
+ * out_pitch_bytes].  Bit-exact with cv2 4.x: (B*3735 + G*19235 + R*9798 + 16384) >> 15.  Device pointers. */
+int bf_bgr2gray(const uint8_t* bgr, int n_frames, int width, int height, size_t in_pitch_bytes, uint8_t* gray,
+                size_t out_pitch_bytes, void* stream);
+
 /* ---- NaN-robust zero-phase band-pass (replaces bandpass_nanrobust, optical_PCA.py:96-121) ------------- */
 
 /* x, y: float64 [n_series, n] on the device (NaN allowed).  sos: HOST float64 [n_sections, 6] in scipy layout

@@ -90,8 +90,12 @@ def test_run_body_axis_flow_core_script_level(tmp_path):
     npz = str(tmp_path / "skel.npz")
     np.savez(npz, time_all=np.arange(T) / 30.0, fps=30.0, ex=ex, ey=ey)
     out_csv = str(tmp_path / "flow.csv")
-    B.run_body_axis_flow_core(vid, npz, spec.roi_polygon(), out_csv, chunk_frames=6)
+    B.run_body_axis_flow_core(vid, npz, spec.roi_polygon(), out_csv, chunk_frames=6)                 # BGR->gray on the GPU
+    host_csv = str(tmp_path / "flow_hostgray.csv")
+    B.run_body_axis_flow_core(vid, npz, spec.roi_polygon(), host_csv, chunk_frames=7, gray_on_device=False)
     df = pd.read_csv(out_csv)
+    assert np.allclose(df[["vx_body", "vy_body", "mag_body"]].to_numpy(),
+                       pd.read_csv(host_csv)[["vx_body", "vy_body", "mag_body"]].to_numpy(), rtol=0, atol=1e-6, equal_nan=True)
     assert list(df.columns) == ["frame", "t_sec", "skel_idx", "axes_ok", "vx_body", "vy_body", "mag_body"]
     assert len(df) == T and df["vx_body"].isna().iloc[0]
     bad = df[df["axes_ok"] == 0]
@@ -112,3 +116,18 @@ def test_run_body_axis_flow_core_script_level(tmp_path):
     got = df[["vx_body", "vy_body", "mag_body"]].to_numpy()
     assert np.array_equal(np.isnan(got), np.isnan(ref))
     assert np.nanmax(np.abs(got - ref)) < 5e-4
+
+
+def test_bgr_to_gray_bit_exact():
+    """cv2.cvtColor(BGR2GRAY) (optical_flow.py:227) on the GPU: bit-exact, odd widths and batches included."""
+    import cv2
+    import torch
+    import btcs_pnes_optical_flow_b200 as B
+    rng = np.random.default_rng(2)
+    for shape in ((3, 120, 160, 3), (1, 67, 91, 3), (2, 1080, 1920, 3), (53, 77, 3)):
+        x = rng.integers(0, 256, shape, dtype=np.uint8)
+        got = B.bgr_to_gray(x)
+        ref = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in x]) if x.ndim == 4 else cv2.cvtColor(x, cv2.COLOR_BGR2GRAY)
+        assert got.dtype == np.uint8 and np.array_equal(got, ref)
+    dev = B.bgr_to_gray(torch.from_numpy(x).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), ref)

@@ -93,3 +93,15 @@ def test_sosfilt_zi_matches_scipy():
         assert np.allclose(pca.sosfilt_zi(sos), sosfilt_zi(sos), rtol=1e-12, atol=1e-14)
     sos = butter(3, 0.2, output="sos")                                       # low-pass: non-zero DC gain chain
     assert np.allclose(pca.sosfilt_zi(sos), sosfilt_zi(sos), rtol=1e-12, atol=1e-14)
+
+
+def test_bgr2gray_fixed_point_formula_matches_cv2():
+    """Pins the 15-bit fixed-point formula the k_bgr2gray kernel implements against cv2.cvtColor (optical_flow.py:227)."""
+    import cv2
+    rng = np.random.default_rng(0)
+    rand = rng.integers(0, 256, (256, 256, 3), dtype=np.uint8)
+    grid = np.stack(np.meshgrid(*[np.arange(0, 256, 5)] * 3, indexing="ij"), -1).reshape(-1, 1, 3).astype(np.uint8)
+    for arr in (rand, grid):
+        b, g, r = (arr[..., i].astype(np.int64) for i in range(3))
+        mine = (b * 3735 + g * 19235 + r * 9798 + 16384) >> 15
+        assert np.array_equal(mine, cv2.cvtColor(arr, cv2.COLOR_BGR2GRAY))
