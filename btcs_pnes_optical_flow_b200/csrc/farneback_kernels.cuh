@@ -2,12 +2,13 @@
 //
 // Algorithm restated from the validated behavioural spec of cv2.calcOpticalFlowFarneback (the single
 // hot call of the reference, /root/reference/optical_flow.py:173; spec in SURVEY.md Appendix A).
-// Data layout in HBM (all float32 unless noted):
-//   level image  I   [frame][h][pitch]
-//   poly coeffs  R   [slot][5][h][pitch]   planes (b_y, b_x, A_yy, A_xx, A_xy)      -- SoA so that both the
-//   matrices     M   [pair][5][h][pitch]   planes (G11, G12, G22, h1, h2)              pointwise reads and the
-//   flow             [pair][h][pitch] float2 (dx, dy)                                  bilinear gather coalesce
-// `pitch` is in elements and a multiple of 32 for plan-owned buffers (128-byte rows).
+// Data layout in HBM:
+//   level image  I   [frame][h][pitch] f32
+//   poly coeffs  R   exact plans:   [slot][5][h][pitch] f32 planes (b_y, b_x, A_yy, A_xx, A_xy)
+//                    compact plans: [slot][h][pitch] x 16 B = 8 x fp16 per pixel (RPix), one LDG.128 per bilinear tap
+//   matrices     M   [pair][5][h][pitch] planes (G11, G12, G22, h1, h2): f32 (exact) or fp16 (compact)
+//   flow             [pair][h][pitch] float2 (dx, dy)
+// `pitch` is in elements and a multiple of 32 for plan-owned buffers.  Kernels templated on RH = compact storage.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -382,23 +383,6 @@ struct ResizeTab {
     const int* iy; const float* ay;  // [h]
 };
 
-// bilinear sample of the coarser flow (cv2.resize INTER_LINEAR, 2 channels) times mult
-__device__ __forceinline__ float2 upsample_flow_px(const float2* __restrict__ fc, int pitch_c, int ws, int hs,
-                                                   const ResizeTab& t, int x, int y, float mult) {
-    const int x0 = t.ix[x], y0 = t.iy[y];
-    const float a = t.ax[x], b = t.ay[y];
-    const int x1 = min(x0 + 1, ws - 1), y1 = min(y0 + 1, hs - 1);
-    const unsigned r0 = (unsigned)y0 * (unsigned)pitch_c, r1 = (unsigned)y1 * (unsigned)pitch_c;
-    const float2 p00 = fc[r0 + (unsigned)x0], p01 = fc[r0 + (unsigned)x1];
-    const float2 p10 = fc[r1 + (unsigned)x0], p11 = fc[r1 + (unsigned)x1];
-    const float h0x = p00.x * (1.f - a) + p01.x * a, h0y = p00.y * (1.f - a) + p01.y * a;
-    const float h1x = p10.x * (1.f - a) + p11.x * a, h1y = p10.y * (1.f - a) + p11.y * a;
-    float2 r;
-    r.x = (h0x * (1.f - b) + h1x * b) * mult;
-    r.y = (h0y * (1.f - b) + h1y * b) * mult;
-    return r;
-}
-
 // K3a: M = UpdateMatrices(R0, R1, flow_init).  flow_mode: 0 = zero, 1 = flow buffer, 2 = upsample coarse.
 struct UpdateArgs {
     const void* R; size_t plane_stride, slot_stride; int slot0, nslots;   // R0 = ring slot (slot0+p), R1 = the next one
@@ -670,16 +654,6 @@ __global__ void k_axes_to_f32(const double* __restrict__ ex, const double* __res
 __global__ void k_fill_nan(float* __restrict__ p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = __int_as_float(0x7fc00000);
-}
-
-// [h][pitch] float2 -> dense [h][w] float2 and back (pitch removal for the cv2-shaped output)
-__global__ void k_copy_flow(const float2* __restrict__ src, int src_pitch, size_t src_stride, float2* __restrict__ dst,
-                            int dst_pitch, size_t dst_stride, int w, int h) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dst_pitch + x] =
-        src[(size_t)blockIdx.z * src_stride + (size_t)y * src_pitch + x];
 }
 
 }  // namespace bf
