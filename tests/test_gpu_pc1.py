@@ -148,3 +148,18 @@ def test_device_bandpass_matches_scipy(golden):
     a = pca.flow_to_pc1(t, g["vx0"], g["vy0"], on_device=True)
     b = pca.flow_to_pc1(t, g["vx0"], g["vy0"], on_device=False)
     assert np.array_equal(np.isnan(a), np.isnan(b)) and np.nanmax(np.abs(a - b)) < 1e-11
+
+
+def test_cli_pca_command_matches_reference_pipeline(tmp_path, golden):
+    """`python -m btcs_pnes_optical_flow_b200 pca`: flow.csv -> flow_pc1.csv, against the reference's PC1 (golden)."""
+    import pandas as pd
+    from btcs_pnes_optical_flow_b200.__main__ import main
+    g = golden("pipeline_golden.npz")
+    rows = g["rows"]
+    pd.DataFrame({"frame": np.arange(len(rows)), "t_sec": g["t"], "vx_body": rows[:, 0], "vy_body": rows[:, 1],
+                  "mag_body": rows[:, 2]}).to_csv(tmp_path / "flow.csv", index=False)
+    assert main(["pca", "--flow", str(tmp_path / "flow.csv"), "--out", str(tmp_path / "flow_pc1.csv")]) == 0
+    df = pd.read_csv(tmp_path / "flow_pc1.csv")
+    assert list(df.columns) == ["t_sec", "pc1_dyn"]
+    got, ref = df["pc1_dyn"].to_numpy(), g["pc1"]
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.nanmax(np.abs(got - ref)) < 1e-10

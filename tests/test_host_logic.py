@@ -105,3 +105,21 @@ def test_bgr2gray_fixed_point_formula_matches_cv2():
         b, g, r = (arr[..., i].astype(np.int64) for i in range(3))
         mine = (b * 3735 + g * 19235 + r * 9798 + 16384) >> 15
         assert np.array_equal(mine, cv2.cvtColor(arr, cv2.COLOR_BGR2GRAY))
+
+
+def test_cli_parser_and_metrics_command(tmp_path, golden):
+    """The CLI keeps the reference scripts' default file names; `metrics` runs on the host without a GPU."""
+    import pandas as pd
+    from btcs_pnes_optical_flow_b200.__main__ import build_parser, main, parse_roi
+    ap = build_parser()
+    a = ap.parse_args(["flow", "--video", "input.mp4", "--npz", "skeleton_pc1.npz", "--roi", "100,100;500,120;520,380;120,400"])
+    assert a.out == "flow.csv" and a.roi.shape == (4, 2) and a.roi[2, 1] == 380.0
+    assert ap.parse_args(["pca"]).flow == "flow.csv" and ap.parse_args(["pca"]).out == "flow_pc1.csv"
+    assert ap.parse_args(["metrics"]).out == "flow_summary_dyn_core.csv"
+    with pytest.raises(Exception):
+        parse_roi("1,2;3,4")
+    g = golden("pipeline_golden.npz")
+    pd.DataFrame({"t_sec": g["t"], "pc1_dyn": g["pc1"]}).to_csv(tmp_path / "flow_pc1.csv", index=False)
+    assert main(["metrics", "--pc1", str(tmp_path / "flow_pc1.csv"), "--out", str(tmp_path / "s.csv")]) == 0
+    row = pd.read_csv(tmp_path / "s.csv").iloc[0]
+    assert row["Peak_n"] == int(g["peak_n"]) and row["PC1_area_0_10"] == pytest.approx(float(g["area"]), rel=1e-9)
