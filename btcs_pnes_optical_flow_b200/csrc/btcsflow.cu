@@ -219,7 +219,7 @@ struct bf_plan {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool use_fast = true;
-    bool r_half = false;        // polynomial coefficients stored as 8 x fp16 per pixel (fast path, uint8 input)
+    bool r_half = false;        // polynomial coefficients packed in 16 B per pixel, b f32 + A f16 (fast path, uint8 input)
     int sm_count = 148;
     // dominant-kernel timing (bf_plan_profile)
     bool prof_on = false;
@@ -1131,3 +1131,12 @@ int bf_stage_upsample_flow(const float* flow_in, int ws, int hs, int w, int h, f
 }
 
 }  // extern "C"
+
+#ifdef BF_TRACE
+// Debug builds only (not declared in include/btcsflow.h): point the phase trace of k_blur_solve_box at a device buffer of
+// 8 x uint64 per CTA of the largest launch, or at nullptr to stop tracing.
+extern "C" int bf_debug_trace_set(void* dev_buf) {
+    unsigned long long* p = static_cast<unsigned long long*>(dev_buf);
+    return cudaMemcpyToSymbol(bf::bf_trace_buf, &p, sizeof(p)) == cudaSuccess ? 0 : -1;
+}
+#endif

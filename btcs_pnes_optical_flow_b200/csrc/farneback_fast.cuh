@@ -39,7 +39,35 @@ struct FastBoxCfg {
     static_assert((size_t)TH * kFbTW * sizeof(float2) <= (size_t)V_FLOATS * sizeof(float), "F must fit in V");
 };
 
+// Debug builds (-DBF_TRACE, tools/trace_phases.py): thread 0 of every CTA of k_blur_solve_box stamps the SM clock at the
+// phase boundaries so that phase durations and the overlap of co-resident CTAs can be read off directly.
+#ifdef BF_TRACE
+__device__ unsigned long long* bf_trace_buf = nullptr;
+__device__ __forceinline__ void trace_stamp(int slot, bool on) {
+    if (threadIdx.x == 0 && on && bf_trace_buf) {
+        const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        unsigned long long t;
+        if (slot == 0) {
+            unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            bf_trace_buf[cta * 8 + 6] = t;
+            bf_trace_buf[cta * 8 + 7] = sm;
+        }
+        bf_trace_buf[cta * 8 + slot] = clock64();
+    }
+}
+#define BF_TRACE_STAMP(k) trace_stamp(k, a.Mout != nullptr)   // launches with the update tail only
+#else
+#define BF_TRACE_STAMP(k)
+#endif
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// One instruction requests a whole contiguous span into L2 through the bulk-copy unit; the per-line form above costs one
+// L1 tag cycle per 128-byte line (~1800 lines per CTA of k_blur_solve_box: ~2700 cycles, 7 % of a CTA's lifetime in the
+// phase trace, profiles/).  p must be 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void prefetch_l2_span(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
@@ -125,9 +153,45 @@ __device__ __forceinline__ void prefetch_r_block(const void* R0v, const void* R1
     }
 }
 
-template <int MH, bool RH, int TH>
-__global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg) {
+// Update tail of one warp: RG rows x 128 columns, lane = column within a 32-wide group, pixel i+1's taps in flight while
+// pixel i is computed.  EDGE: the tile may stick out of the image or touch the 5-px attenuation ring.
+template <bool EDGE, int RG, typename MT, typename RowFn, typename ColFn>
+__device__ __forceinline__ void update_tail_pipelined(const uint4* __restrict__ R0, const uint4* __restrict__ R1,
+                                                      const float2* __restrict__ F, MT* __restrict__ Mo, unsigned plane,
+                                                      unsigned pitch, int w, int h, int x0, int y0, RowFn tail_row, ColFn tail_col) {
+    constexpr int N = 4 * RG;
+    auto issue = [&](int i, UpdTaps& t) {
+        const int r = tail_row(i), cx = tail_col(i);
+        const float2 f = F[r * kFbTW + cx];
+        int x = x0 + cx, y = y0 + r;
+        if (EDGE) { x = min(x, w - 1); y = min(y, h - 1); }
+        update_issue_h(R0, R1, pitch, w, h, x, y, f.x, f.y, t);
+    };
+    auto finish = [&](int i, const UpdTaps& t) {
+        const int r = tail_row(i), cx = tail_col(i);
+        const int x = x0 + cx, y = y0 + r;
+        float mm[5];
+        update_finish_h<EDGE>(t, w, h, x, y, mm);
+        if (!EDGE || (x < w && y < h)) store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, mm);
+    };
+    UpdTaps A, B;
+    issue(0, A);
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        issue(i + 1, B);
+        finish(i, A);
+        if (i + 2 < N) issue(i + 2, A);
+        finish(i + 1, B);
+    }
+}
+
+// NW warps per CTA (TH % NW == 0): 8 -> 80 registers per thread at 3 CTAs/SM; 6 -> 112 registers and phase 1's 180 column
+// tasks fill 94 % of the threads instead of 70 %.
+template <int MH, bool RH, int TH, int NW = 8>
+__global__ void __launch_bounds__(NW * 32, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg, const bool tail_pipelined) {
     using C = FastBoxCfg<MH, TH>;
+    constexpr int NT = NW * 32, RG = TH / NW;
+    static_assert(TH % NW == 0 && NW <= 8, "rows must split evenly over the warps");
     extern __shared__ __align__(16) float smem[];
     float* V = smem;                                   // [5][TH][VP]
     float2* F = reinterpret_cast<float2*>(smem);       // [TH][TW], aliases V after phase 2
@@ -139,16 +203,49 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
     using MT = typename MStore<RH>::type;
     const MT* Mp = static_cast<const MT*>(a.M) + (size_t)p * a.m_stride;
     constexpr int kLine = 128 / (int)sizeof(MT);                          // elements per 128-byte line
+    BF_TRACE_STAMP(0);
 
     // A lone CTA of this kernel takes ~22 us (ncu, profiles/): its time is a chain of HBM round trips, not bandwidth.
     // So the whole M tile (with halo) is requested into L2 up front -- phase 1's register-window stream then pays L2
     // latency per step -- and likewise what phase 3 will read (R0 under the tile, R1 around it), which travels from
     // HBM while phases 1-2 run.
-    {
+    // Rows of M and of packed R are 16-byte aligned spans (plan pitch is a multiple of 32 elements): one bulk request per
+    // row.  Other layouts (stage API with odd pitches, fp32 R planes) keep the per-line requests.
+    const bool span_ok = ((pitch | plane | (unsigned)a.m_stride) & (16 / (unsigned)sizeof(MT) - 1)) == 0;
+    const void* R0 = nullptr;
+    const void* R1 = nullptr;
+    if (a.Mout) {
+        R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
+        R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
+    }
+    if (span_ok) {
+        constexpr int NROW = TH + 2 * MH;
+        const int xs = max(x0 - C::HALO, 0), xe = min(x0 + kFbTW + C::HALO, w);
+        const unsigned mbytes = ((unsigned)(xe - xs) * (unsigned)sizeof(MT) + 15u) & ~15u;
+        for (int e = tid; e < 5 * NROW; e += NT) {
+            const int c = e / NROW, r = e - c * NROW;
+            const int yy = min(max(y0 - MH + r, 0), h - 1);
+            prefetch_l2_span(Mp + (size_t)c * plane + (unsigned)yy * pitch + (unsigned)xs, mbytes);
+        }
+        if (RH && a.Mout) {
+            const uint4* R0h = static_cast<const uint4*>(R0);
+            const uint4* R1h = static_cast<const uint4*>(R1);
+            const int xe0 = min(x0 + kFbTW, w), xs1 = max(x0 - 32, 0), xe1 = min(x0 + kFbTW + 32, w);
+            // the last threads first: the M rows above went to the first 5 * NROW threads
+            for (int e = NT - 1 - tid; e < 2 * TH + 4; e += NT) {
+                if (e < TH) {
+                    prefetch_l2_span(R0h + (unsigned)min(y0 + e, h - 1) * pitch + (unsigned)x0, (unsigned)(xe0 - x0) * 16u);
+                } else {
+                    const int yy = min(max(y0 - 2 + (e - TH), 0), h - 1);
+                    prefetch_l2_span(R1h + (unsigned)yy * pitch + (unsigned)xs1, (unsigned)(xe1 - xs1) * 16u);
+                }
+            }
+        }
+    } else {
         constexpr int NL = (kFbTW + 2 * C::HALO + kLine - 1) / kLine + 1;            // lines per tile row (incl. misalignment)
         constexpr int NROW = TH + 2 * MH;
         const int xlo = max(x0 - C::HALO, 0) & ~(kLine - 1), xmaxl = max((w - 1) & ~(kLine - 1), 0);
-        for (int e = tid; e < NROW * NL; e += 256) {
+        for (int e = tid; e < NROW * NL; e += NT) {
             const int r = e / NL, l = e - r * NL;
             const int yy = min(max(y0 - MH + r, 0), h - 1), xx = min(xlo + l * kLine, xmaxl);
             const MT* q = Mp + (unsigned)yy * pitch + (unsigned)xx;
@@ -156,20 +253,15 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
             for (int c = 0; c < 5; ++c) prefetch_l2(q + (size_t)c * plane);
         }
     }
-    const void* R0 = nullptr;
-    const void* R1 = nullptr;
-    if (a.Mout) {
-        R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
-        R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
-        prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, 256);
-    }
+    if (a.Mout && !(RH && span_ok)) prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, NT);
 
+    BF_TRACE_STAMP(1);
     // ---------------- phase 1: vertical sums ----------------
     // w % 4 == 0 and float4-aligned columns: a float4 column is entirely inside the image, entirely left of it or
     // entirely right of it.  Outside columns load the nearest inside chunk and splat its edge lane when the SUM is
     // stored (replicate border; splat commutes with the sum), so the load path is branch-free.
     const bool rows_in = (y0 - MH >= 0) && (y0 + TH + MH <= h);      // block-uniform: no row clamping needed
-    for (int task = tid; task < 5 * C::NC4; task += 256) {
+    for (int task = tid; task < 5 * C::NC4; task += NT) {
         const int c = task / C::NC4, q = task - c * C::NC4;
         const int gx = x0 - C::HALO + 4 * q;
         const int mode = gx < 0 ? 1 : (gx >= w ? 2 : 0);
@@ -182,13 +274,14 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
         else vertical_box_sums<MH, false, true, TH, C::PF>(src, pitch, y0 - MH, h, mode, dst, C::VP);
     }
     __syncthreads();
+    BF_TRACE_STAMP(2);
 
     // ---------------- phase 2: horizontal sums + solve ----------------
     const int g = tid & 31, rb = tid >> 5;
-    float2 fl[C::RG][4];
+    float2 fl[RG][4];
 #pragma unroll
-    for (int k = 0; k < C::RG; ++k) {
-        const int r = rb + 8 * k;
+    for (int k = 0; k < RG; ++k) {
+        const int r = rb + NW * k;
         float gs[5][4];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
@@ -223,24 +316,35 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
     }
     __syncthreads();                                    // all reads of V done before F overwrites it
 #pragma unroll
-    for (int k = 0; k < C::RG; ++k) {
-        float4* fp = reinterpret_cast<float4*>(F + (rb + 8 * k) * kFbTW + 4 * g);
+    for (int k = 0; k < RG; ++k) {
+        float4* fp = reinterpret_cast<float4*>(F + (rb + NW * k) * kFbTW + 4 * g);
         fp[0] = make_float4(fl[k][0].x, fl[k][0].y, fl[k][1].x, fl[k][1].y);
         fp[1] = make_float4(fl[k][2].x, fl[k][2].y, fl[k][3].x, fl[k][3].y);
     }
     __syncthreads();
+    BF_TRACE_STAMP(3);
 
     // ---------------- phase 3: coalesced tail ----------------
+    // A warp walks DOWN one 32-pixel column group (NW = 8: 4 column groups x 2 row halves): the bottom taps of row r are
+    // the top taps of row r + 1, so consecutive iterations of the same warp hit L1 (which is only 228 - 3 x 71 = 15 KB here)
+    // instead of fetching every R1 line twice from L2.
     const int lane = tid & 31, wid = tid >> 5;
+    constexpr bool kColWalk = (NW % 4) == 0;
+    const int tail_r0 = kColWalk ? (wid >> 2) * (4 * RG) : wid * RG, tail_c0 = kColWalk ? (wid & 3) * 32 + lane : lane;
+    auto tail_row = [&](int i) { return kColWalk ? tail_r0 + i : tail_r0 + (i >> 2); };
+    auto tail_col = [&](int i) { return kColWalk ? tail_c0 : tail_c0 + (i & 3) * 32; };
     if (a.flow || a.Mout) {
         float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
         MT* Mo = a.Mout ? static_cast<MT*>(a.Mout) + (size_t)p * a.m_stride : nullptr;
         // interior tiles (85 % at 1080p): bounds and the 5-px attenuation ring are decided once per tile
         const bool inner = (x0 >= 5) && (y0 >= 5) && (x0 + kFbTW <= w - 5) && (y0 + TH <= h - 5);
-        if (inner && Mo && !fo) {
+        if (RH && Mo && !fo && tail_pipelined) {
+            if (inner) update_tail_pipelined<false, RG>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, plane, pitch, w, h, x0, y0, tail_row, tail_col);
+            else update_tail_pipelined<true, RG>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, plane, pitch, w, h, x0, y0, tail_row, tail_col);
+        } else if (inner && Mo && !fo) {
 #pragma unroll 4
-            for (int i = 0; i < 4 * C::RG; ++i) {
-                const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
+            for (int i = 0; i < 4 * RG; ++i) {
+                const int r = tail_row(i), cx = tail_col(i);
                 const int x = x0 + cx, y = y0 + r;
                 const float2 f = F[r * kFbTW + cx];
                 float mm[5];
@@ -249,8 +353,8 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
             }
         } else
 #pragma unroll 4
-        for (int i = 0; i < 4 * C::RG; ++i) {
-            const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
+        for (int i = 0; i < 4 * RG; ++i) {
+            const int r = tail_row(i), cx = tail_col(i);
             const int x = x0 + cx, y = y0 + r;
             if (x < w && y < h) {
                 const float2 f = F[r * kFbTW + cx];
@@ -263,6 +367,10 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
             }
         }
     }
+#ifdef BF_TRACE
+    __syncthreads();
+    BF_TRACE_STAMP(4);
+#endif
     if (a.partial) {
         const float* ax = a.axes + p * 4;
         const float e00 = ax[0], e01 = ax[1], e10 = ax[2], e11 = ax[3];
@@ -271,8 +379,8 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
             const uint8_t* mk = a.masks + (size_t)roi * a.mask_stride;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 4
-            for (int i = 0; i < 4 * C::RG; ++i) {
-                const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
+            for (int i = 0; i < 4 * RG; ++i) {
+                const int r = tail_row(i), cx = tail_col(i);
                 const int x = x0 + cx, y = y0 + r;
                 if (x < w && y < h && mk[(size_t)y * a.mask_pitch + x] != 0) {
                     const float2 f = F[r * kFbTW + cx];
@@ -288,7 +396,7 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_bo
             if (tid < 4) {
                 float t = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) t += s_red[i * 4 + tid];
+                for (int i = 0; i < NW; ++i) t += s_red[i * 4 + tid];
                 a.partial[(((size_t)p * a.n_roi + roi) * ncta + cta) * kRoiVals + tid] = t;
             }
         }
@@ -482,9 +590,9 @@ inline bool blur_solve_fast_supported(const WinCoef& wc, int pitch) {
     return !wc.gauss && wc.m == 7 && (pitch % 4) == 0;
 }
 // + the image width must be a multiple of 4 (float4 columns are all-inside or all-outside) and at least one chunk
-inline bool blur_solve_fast_shape(int w) { return (w % 4) == 0 && w >= 4; }
+inline bool blur_solve_fast_shape(int w, int h) { return (w % 4) == 0 && w >= 4 && h >= 2; }
 inline bool blur_solve_fast_aligned(const BlurSolveArgs& a) {
-    return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0 && blur_solve_fast_shape(a.w);
+    return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0 && blur_solve_fast_shape(a.w, a.h);
 }
 // Tile height: 32 rows = 95 KB shared -> 2 CTAs/SM; 24 rows = 71 KB -> 3 CTAs/SM (default: the kernel is latency-bound,
 // more resident CTAs win over the extra vertical halo; measured in profiles/); 16 rows -> 4 CTAs/SM.
@@ -495,21 +603,31 @@ inline int tile_th() {
 }
 inline int blur_solve_fast_ncta(int w, int h) { const int th = tile_th(); return ((w + kFbTW - 1) / kFbTW) * ((h + th - 1) / th); }
 
-template <bool RH, int TH>
+inline bool tail_pipelined() {
+    const char* e = getenv("BTCSFLOW_TAIL");
+    return !(e && e[0] == 's');          // "serial" selects the one-piece update tail (A/B experiments; 1.4 % slower)
+}
+inline int tile_warps() {
+    const char* e = getenv("BTCSFLOW_TILE_WARPS");
+    return (e && atoi(e) == 6) ? 6 : 8;
+}
+template <bool RH, int TH, int NW = 8>
 inline void launch_blur_solve_fast_th(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
     using C = FastBoxCfg<7, TH>;
     // per device/context attribute; cheap enough to set on every launch (one process may own several plans)
-    cudaFuncSetAttribute(k_blur_solve_box<7, RH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaFuncSetAttribute(k_blur_solve_box<7, RH, TH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     const float reg = 1e-3f / (wc.scale * wc.scale);
     dim3 g((a.w + kFbTW - 1) / kFbTW, (a.h + TH - 1) / TH, np);
-    k_blur_solve_box<7, RH, TH><<<g, 256, C::SMEM, st>>>(a, reg);
+    k_blur_solve_box<7, RH, TH, NW><<<g, NW * 32, C::SMEM, st>>>(a, reg, tail_pipelined());
 }
 template <bool RH>
 inline void launch_blur_solve_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
     switch (tile_th()) {
         case 16: launch_blur_solve_fast_th<RH, 16>(a, wc, np, st); break;
         case 32: launch_blur_solve_fast_th<RH, 32>(a, wc, np, st); break;
-        default: launch_blur_solve_fast_th<RH, 24>(a, wc, np, st);
+        default:
+            if (tile_warps() == 6) launch_blur_solve_fast_th<RH, 24, 6>(a, wc, np, st);
+            else launch_blur_solve_fast_th<RH, 24>(a, wc, np, st);
     }
 }
 inline void launch_blur_solve_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st) {

@@ -5,7 +5,7 @@
 // Data layout in HBM:
 //   level image  I   [frame][h][pitch] f32
 //   poly coeffs  R   exact plans:   [slot][5][h][pitch] f32 planes (b_y, b_x, A_yy, A_xx, A_xy)
-//                    compact plans: [slot][h][pitch] x 16 B = 8 x fp16 per pixel (RPix), one LDG.128 per bilinear tap
+//                    compact plans: [slot][h][pitch] x 16 B per pixel (RPix: b in fp32, A in fp16), one LDG.128 per bilinear tap
 //   matrices     M   [pair][5][h][pitch] planes (G11, G12, G22, h1, h2): f32 (exact) or fp16 (compact)
 //   flow             [pair][h][pitch] float2 (dx, dy)
 // `pitch` is in elements and a multiple of 32 for plan-owned buffers.  Kernels templated on RH = compact storage.
@@ -289,26 +289,26 @@ __device__ __forceinline__ void store_m(MT* __restrict__ M, unsigned plane, unsi
     for (int c = 0; c < 5; ++c) { m_from_float(pm, m[c]); pm += plane; }
 }
 
-// ---- packed polynomial coefficients: 8 x fp16 per pixel (5 used), one 128-bit load per bilinear tap --------------
-// Storage format only: all arithmetic stays fp32.  fp16 storage of R costs <= 5e-4 px max / 6e-5 px mean endpoint error
-// against cv2 (tests/test_gpu_flow.py), 100x inside the parity gate, and turns the 20 scalar gather
-// loads + 5 centre loads per pixel into 4 + 1 LDG.128.  Used for uint8 input only (|R| is bounded by the 0..255 range).
-struct __align__(16) RPix { __half2 a, b, c, d; };   // (b_y, b_x), (A_yy, A_xx), (A_xy, 0), (0, 0)
+// ---- packed polynomial coefficients: 16 bytes per pixel, one 128-bit load per bilinear tap ------------------------
+// Storage format only: all arithmetic stays fp32.  The linear terms b (whose frame-to-frame DIFFERENCE drives the flow)
+// stay fp32; the quadratic terms A, which only enter through averages, are fp16: (b_y f32, b_x f32, (A_yy, A_xx) f16x2,
+// (A_xy, 0) f16x2).  Against the earlier all-fp16 pixel this unpacks with 3 conversions per tap instead of 5 and removes
+// most of the storage error (tests/test_gpu_flow.py).  It turns the 20 scalar gather loads + 5 centre
+// loads per pixel of the planar layout into 4 + 1 LDG.128.  Used for uint8 input only (|A| is bounded by the 0..255 range).
+struct __align__(16) RPix { float by, bx; __half2 ayy_axx, axy_0; };
 
 __device__ __forceinline__ uint4 pack_r(float r0, float r1, float r2, float r3, float r4) {
-    union { uint4 u; __half2 h[4]; } t;
-    t.h[0] = __floats2half2_rn(r0, r1);
-    t.h[1] = __floats2half2_rn(r2, r3);
-    t.h[2] = __floats2half2_rn(r4, 0.f);
-    t.h[3] = __floats2half2_rn(0.f, 0.f);
-    return t.u;
+    union { unsigned v; __half2 h; } a, b;
+    a.h = __floats2half2_rn(r2, r3);
+    b.h = __floats2half2_rn(r4, 0.f);
+    return make_uint4(__float_as_uint(r0), __float_as_uint(r1), a.v, b.v);
 }
 
 __device__ __forceinline__ void unpack_r(const uint4& u, float v[5]) {
-    union { uint4 u; __half2 h[4]; } t;
-    t.u = u;
-    const float2 a = __half22float2(t.h[0]), b = __half22float2(t.h[1]);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = __low2float(t.h[2]);
+    union { unsigned v; __half2 h; } a, b;
+    a.v = u.z; b.v = u.w;
+    const float2 q = __half22float2(a.h);
+    v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = q.x; v[3] = q.y; v[4] = __low2float(b.h);
 }
 
 // UpdateMatrices for one pixel from packed R (same arithmetic as update_px).  R0/R1 point at pixel (0,0) of the frame.
@@ -346,6 +346,57 @@ __device__ __forceinline__ void update_px_h(const uint4* __restrict__ R0, const 
     r3 = (q[1] - r3) * 0.5f;
     r2 += r4 * dy + r6 * dx;
     r3 += r6 * dy + r5 * dx;
+    if (BORDER && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
+        const float sc = border_w(x, w) * border_w(y, h);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    out[0] = r4 * r4 + r6 * r6;
+    out[1] = (r4 + r5) * r6;
+    out[2] = r5 * r5 + r6 * r6;
+    out[3] = r4 * r2 + r6 * r3;
+    out[4] = r6 * r2 + r5 * r3;
+}
+
+// The same update split in two so that the gather of the NEXT pixel is in flight while this one is being computed (the
+// one-piece version issues its four taps inside the `inside` branch, so every pixel pays a full L2 round trip in series;
+// ncu source page, profiles/).  Branch-free: the taps are always fetched from a clamped footprint (requires w, h >= 2)
+// and the fallback branch becomes five selects.  Arithmetic and operation order are those of update_px_h.
+struct UpdTaps { uint4 q, u00, u01, u10, u11; float fx, fy, dx, dy; bool inside; };
+
+__device__ __forceinline__ void update_issue_h(const uint4* __restrict__ R0, const uint4* __restrict__ R1, unsigned pitch,
+                                               int w, int h, int x, int y, float dx, float dy, UpdTaps& t) {
+    t.q = __ldg(R0 + (unsigned)y * pitch + (unsigned)x);
+    const float fx = (float)x + dx, fy = (float)y + dy;
+    const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+    t.fx = fx - (float)x1;
+    t.fy = fy - (float)y1;
+    t.dx = dx; t.dy = dy;
+    t.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+    const int cx = min(max(x1, 0), w - 2), cy = min(max(y1, 0), h - 2);
+    const uint4* pa = R1 + (unsigned)cy * pitch + (unsigned)cx;
+    t.u00 = __ldg(pa); t.u01 = __ldg(pa + 1); t.u10 = __ldg(pa + pitch); t.u11 = __ldg(pa + pitch + 1);
+}
+
+template <bool BORDER>
+__device__ __forceinline__ void update_finish_h(const UpdTaps& t, int w, int h, int x, int y, float out[5]) {
+    float q[5], t00[5], t01[5], t10[5], t11[5];
+    unpack_r(t.q, q);
+    unpack_r(t.u00, t00); unpack_r(t.u01, t01); unpack_r(t.u10, t10); unpack_r(t.u11, t11);
+    const float fx = t.fx, fy = t.fy;
+    const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+    float rw[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) rw[c] = a00 * t00[c] + a01 * t01[c] + a10 * t10[c] + a11 * t11[c];
+    const bool in = t.inside;
+    float r2 = in ? rw[0] : 0.f;
+    float r3 = in ? rw[1] : 0.f;
+    float r4 = in ? (q[2] + rw[2]) * 0.5f : q[2];
+    float r5 = in ? (q[3] + rw[3]) * 0.5f : q[3];
+    float r6 = in ? (q[4] + rw[4]) * 0.25f : q[4] * 0.5f;
+    r2 = (q[0] - r2) * 0.5f;
+    r3 = (q[1] - r3) * 0.5f;
+    r2 += r4 * t.dy + r6 * t.dx;
+    r3 += r6 * t.dy + r5 * t.dx;
     if (BORDER && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
         const float sc = border_w(x, w) * border_w(y, h);
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
@@ -423,13 +474,14 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     if (a.flow_mode == 2) { ux0 = a.tab.ix[x]; ua = a.tab.ax[x]; ux1 = min(ux0 + 1, a.ws - 1); }
     // a block of rows away from the 5-px ring needs no attenuation test (block-uniform)
     const bool inner = (x >= 5) && (x < w - 5) && (yb >= 5) && (yb + kUpdRows <= h - 5);
+    // flow_init of the thread's rows first (independent loads), then the updates
+    float2 fl[kUpdRows];
 #pragma unroll
     for (int k = 0; k < kUpdRows; ++k) {
-        const int y = yb + k;
-        if (y >= h) break;
-        float2 fl = make_float2(0.f, 0.f);
+        const int y = min(yb + k, h - 1);
+        fl[k] = make_float2(0.f, 0.f);
         if (a.flow_mode == 1) {
-            fl = fin[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x];
+            fl[k] = fin[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x];
         } else if (a.flow_mode == 2) {
             // bilinear sample of the coarser flow (cv2.resize INTER_LINEAR) times mult
             const int y0 = a.tab.iy[y], y1 = min(y0 + 1, a.hs - 1);
@@ -439,16 +491,38 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
             const float2 p10 = fin[r1 + (unsigned)ux0], p11 = fin[r1 + (unsigned)ux1];
             const float h0x = p00.x * (1.f - ua) + p01.x * ua, h0y = p00.y * (1.f - ua) + p01.y * ua;
             const float h1x = p10.x * (1.f - ua) + p11.x * ua, h1y = p10.y * (1.f - ua) + p11.y * ua;
-            fl.x = (h0x * (1.f - b) + h1x * b) * a.mult;
-            fl.y = (h0y * (1.f - b) + h1y * b) * a.mult;
+            fl[k].x = (h0x * (1.f - b) + h1x * b) * a.mult;
+            fl[k].y = (h0y * (1.f - b) + h1y * b) * a.mult;
         }
-        if (fout) fout[(unsigned)y * (unsigned)a.flow_out_pitch + (unsigned)x] = fl;
-        if (Mo) {
+        if (fout && yb + k < h) fout[(unsigned)y * (unsigned)a.flow_out_pitch + (unsigned)x] = fl[k];
+    }
+    if (!Mo) return;
+    if (RH && w >= 2 && h >= 2) {
+        // packed coefficients: row k+1's taps are in flight while row k is computed (update_issue_h / update_finish_h)
+        const uint4* R0h = static_cast<const uint4*>(R0);
+        const uint4* R1h = static_cast<const uint4*>(R1);
+        UpdTaps A, B;
+        update_issue_h(R0h, R1h, pitch, w, h, x, min(yb, h - 1), fl[0].x, fl[0].y, A);
+#pragma unroll
+        for (int k = 0; k < kUpdRows; k += 2) {
+            update_issue_h(R0h, R1h, pitch, w, h, x, min(yb + k + 1, h - 1), fl[k + 1].x, fl[k + 1].y, B);
             float m[5];
-            if (inner) update_px_any<RH, false>(R0, R1, plane, pitch, w, h, x, y, fl.x, fl.y, m);
-            else update_px_any<RH, true>(R0, R1, plane, pitch, w, h, x, y, fl.x, fl.y, m);
-            store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, m);
+            if (inner) update_finish_h<false>(A, w, h, x, yb + k, m); else update_finish_h<true>(A, w, h, x, yb + k, m);
+            if (yb + k < h) store_m(Mo, plane, (unsigned)(yb + k) * pitch + (unsigned)x, m);
+            if (k + 2 < kUpdRows) update_issue_h(R0h, R1h, pitch, w, h, x, min(yb + k + 2, h - 1), fl[k + 2].x, fl[k + 2].y, A);
+            if (inner) update_finish_h<false>(B, w, h, x, yb + k + 1, m); else update_finish_h<true>(B, w, h, x, yb + k + 1, m);
+            if (yb + k + 1 < h) store_m(Mo, plane, (unsigned)(yb + k + 1) * pitch + (unsigned)x, m);
         }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < kUpdRows; ++k) {
+        const int y = yb + k;
+        if (y >= h) break;
+        float m[5];
+        if (inner) update_px_any<RH, false>(R0, R1, plane, pitch, w, h, x, y, fl[k].x, fl[k].y, m);
+        else update_px_any<RH, true>(R0, R1, plane, pitch, w, h, x, y, fl[k].x, fl[k].y, m);
+        store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, m);
     }
 }
 
