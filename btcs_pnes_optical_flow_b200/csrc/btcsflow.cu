@@ -185,6 +185,9 @@ struct ScaleInfo {
     float* tmpk = nullptr;                    // horizontal-pass scratch of this level [F][H][pitch] (levels coarser than 0)
     void* R = nullptr;                        // fp32 planes [F][5][h][pitch], or packed fp16 pixels [F][h][pitch] x 16 B
     float2* flow = nullptr;                   // [B][h][pitch]
+    // tensor maps for the tile kernel's L2 prefetch (compact plans): one per matrices buffer
+    bf::TileMaps maps[2];
+    int maps_th = 0;                          // tile height they were encoded for; 0 = none
 };
 
 template <typename T>
@@ -334,13 +337,13 @@ int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, b
 }
 
 int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast, bool r_half,
-                      cudaStream_t st) {
+                      cudaStream_t st, const bf::TileMaps* maps = nullptr, int maps_th = 0) {
     switch (choose_blur_kernel(a, wc, allow_fast)) {
         case BK_MARCH:
             bf::launch_march(a, wc, np, sm_count_cached(), r_half, st);
             break;
         case BK_TILE:
-            bf::launch_blur_solve_fast(a, wc, np, r_half, st);
+            bf::launch_blur_solve_fast(a, wc, np, r_half, st, maps, maps_th);
             break;
         case BK_GAUSS:
             bf::launch_gauss_fast(a, wc, np, r_half, st);
@@ -506,7 +509,7 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
                 }
                 CU(cudaEventRecord(p->prof_ev[p->prof_used], st));
             }
-            rc = launch_blur_solve(a, p->wc, np, p->use_fast, p->r_half, st);
+            rc = launch_blur_solve(a, p->wc, np, p->use_fast, p->r_half, st, s.maps_th ? &s.maps[it & 1] : nullptr, s.maps_th);
             if (rc) return rc;
             if (prof) {
                 CU(cudaEventRecord(p->prof_ev[p->prof_used + 1], st));
@@ -656,6 +659,19 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
         if ((rc = plan_alloc(p, &mbuf, mbytes))) return cleanup_fail(rc);
         cudaMemset(mbuf, 0, mbytes);
         p->M[i] = mbuf;
+    }
+    // Tensor maps for the tile kernel's L2 prefetch (compact plans; BTCSFLOW_TMAP=0 keeps the per-row requests).
+    {
+        const char* e = getenv("BTCSFLOW_TMAP");
+        if (p->r_half && p->use_fast && !(e && e[0] == '0')) {
+            const int th = bf::tile_th();
+            for (auto& s : p->sc) {
+                if (!bf::blur_solve_fast_shape(s.w, s.h)) continue;
+                if (bf::encode_tile_maps(&s.maps[0], p->M[0], s.R, s.w, s.h, s.pitch, s.plane, p->B, p->F, th) &&
+                    bf::encode_tile_maps(&s.maps[1], p->M[1], s.R, s.w, s.h, s.pitch, s.plane, p->B, p->F, th))
+                    s.maps_th = th;
+            }
+        }
     }
     if ((rc = plan_alloc(p, &p->axes, (size_t)p->B * 4))) return cleanup_fail(rc);
     p->ncta_max = std::max({cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), cdiv(fine.w, bf::kFbTW) * cdiv(fine.h, 16),

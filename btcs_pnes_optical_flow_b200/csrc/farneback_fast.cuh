@@ -14,6 +14,9 @@
 //            loads, bilinear R1 gather, M' stores; ROI sums reduced per CTA (deterministic partials).
 #pragma once
 #include <cstdlib>
+#include <cstring>
+
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "farneback_kernels.cuh"
 
@@ -68,6 +71,17 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ void prefetch_l2_span(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// A whole 4-D box (tile of M with its halo: x, y, channel, pair; block of R: 4 words, x, y, ring slot) requested into L2
+// by ONE instruction through a tensor map; parts of the box outside the tensor are skipped by the hardware.
+__device__ __forceinline__ void prefetch_l2_box(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// Tensor maps of one launch of k_blur_solve_box (built per scale at plan creation, bf::encode_tile_maps in btcsflow.cu):
+// m = input matrices {x, y, 5 channels, pair}, box (TW + 2 HALO) x (TH + 2 MH) x 5 x 1; r0 / r1 = packed R ring
+// {128 words = 32 pixels, x / 32, y, slot}, boxes 128 x 4 x TH x 1 and 128 x 6 x (TH + 4) x 1.
+struct TileMaps { CUtensorMap m, r0, r1; };
+
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
@@ -188,7 +202,8 @@ __device__ __forceinline__ void update_tail_pipelined(const uint4* __restrict__ 
 // NW warps per CTA (TH % NW == 0): 8 -> 80 registers per thread at 3 CTAs/SM; 6 -> 112 registers and phase 1's 180 column
 // tasks fill 94 % of the threads instead of 70 %.
 template <int MH, bool RH, int TH, int NW = 8>
-__global__ void __launch_bounds__(NW * 32, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg, const bool tail_pipelined) {
+__global__ void __launch_bounds__(NW * 32, FastBoxCfg<MH, TH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg, const bool tail_pipelined, const bool use_maps,
+                                                                                 const __grid_constant__ TileMaps maps) {
     using C = FastBoxCfg<MH, TH>;
     constexpr int NT = NW * 32, RG = TH / NW;
     static_assert(TH % NW == 0 && NW <= 8, "rows must split evenly over the warps");
@@ -218,7 +233,16 @@ __global__ void __launch_bounds__(NW * 32, FastBoxCfg<MH, TH>::CTAS) k_blur_solv
         R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
         R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
     }
-    if (span_ok) {
+    if (use_maps) {
+        // three instructions per CTA instead of ~1800 per-line requests (7 % of a CTA's lifetime in the phase trace)
+        if (tid == 0) {
+            prefetch_l2_box(&maps.m, x0 - C::HALO, y0 - MH, 0, p);
+            if (a.Mout) {
+                prefetch_l2_box(&maps.r0, 0, x0 / 32, y0, ring_slot(a.slot0, p, a.nslots));
+                prefetch_l2_box(&maps.r1, 0, x0 / 32 - 1, y0 - 2, ring_slot(a.slot0, p + 1, a.nslots));
+            }
+        }
+    } else if (span_ok) {
         constexpr int NROW = TH + 2 * MH;
         const int xs = max(x0 - C::HALO, 0), xe = min(x0 + kFbTW + C::HALO, w);
         const unsigned mbytes = ((unsigned)(xe - xs) * (unsigned)sizeof(MT) + 15u) & ~15u;
@@ -253,7 +277,7 @@ __global__ void __launch_bounds__(NW * 32, FastBoxCfg<MH, TH>::CTAS) k_blur_solv
             for (int c = 0; c < 5; ++c) prefetch_l2(q + (size_t)c * plane);
         }
     }
-    if (a.Mout && !(RH && span_ok)) prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, NT);
+    if (a.Mout && !use_maps && !(RH && span_ok)) prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, NT);
 
     BF_TRACE_STAMP(1);
     // ---------------- phase 1: vertical sums ----------------
@@ -612,27 +636,80 @@ inline int tile_warps() {
     return (e && atoi(e) == 6) ? 6 : 8;
 }
 template <bool RH, int TH, int NW = 8>
-inline void launch_blur_solve_fast_th(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
+inline void launch_blur_solve_fast_th(const BlurSolveArgs& a, const WinCoef& wc, int np, const TileMaps* maps, cudaStream_t st) {
     using C = FastBoxCfg<7, TH>;
     // per device/context attribute; cheap enough to set on every launch (one process may own several plans)
     cudaFuncSetAttribute(k_blur_solve_box<7, RH, TH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     const float reg = 1e-3f / (wc.scale * wc.scale);
     dim3 g((a.w + kFbTW - 1) / kFbTW, (a.h + TH - 1) / TH, np);
-    k_blur_solve_box<7, RH, TH, NW><<<g, NW * 32, C::SMEM, st>>>(a, reg, tail_pipelined());
+    static const TileMaps none{};
+    k_blur_solve_box<7, RH, TH, NW><<<g, NW * 32, C::SMEM, st>>>(a, reg, tail_pipelined(), maps != nullptr, maps ? *maps : none);
 }
+// maps (optional): tensor maps encoded for tile height maps_th; ignored when another tile height is selected.
 template <bool RH>
-inline void launch_blur_solve_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
-    switch (tile_th()) {
-        case 16: launch_blur_solve_fast_th<RH, 16>(a, wc, np, st); break;
-        case 32: launch_blur_solve_fast_th<RH, 32>(a, wc, np, st); break;
+inline void launch_blur_solve_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, const TileMaps* maps, int maps_th,
+                                     cudaStream_t st) {
+    const int th = tile_th();
+    if (!RH || maps_th != th) maps = nullptr;
+    switch (th) {
+        case 16: launch_blur_solve_fast_th<RH, 16>(a, wc, np, maps, st); break;
+        case 32: launch_blur_solve_fast_th<RH, 32>(a, wc, np, maps, st); break;
         default:
-            if (tile_warps() == 6) launch_blur_solve_fast_th<RH, 24, 6>(a, wc, np, st);
-            else launch_blur_solve_fast_th<RH, 24>(a, wc, np, st);
+            if (tile_warps() == 6) launch_blur_solve_fast_th<RH, 24, 6>(a, wc, np, maps, st);
+            else launch_blur_solve_fast_th<RH, 24>(a, wc, np, maps, st);
     }
 }
-inline void launch_blur_solve_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st) {
-    if (r_half) launch_blur_solve_fast_t<true>(a, wc, np, st);
-    else launch_blur_solve_fast_t<false>(a, wc, np, st);
+inline void launch_blur_solve_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st,
+                                   const TileMaps* maps = nullptr, int maps_th = 0) {
+    if (r_half) launch_blur_solve_fast_t<true>(a, wc, np, maps, maps_th, st);
+    else launch_blur_solve_fast_t<false>(a, wc, np, nullptr, 0, st);
+}
+
+// Host side: encode the three tensor maps of one scale for tile height th.  M: fp16 planes [pair][5][h][pitch] at `M`;
+// R: packed pixels [slot][h][pitch] x 16 B.  Returns false (maps unused, per-row prefetch instead) if the driver entry
+// point is missing or rejects the layout.
+inline bool encode_tile_maps(TileMaps* out, const void* M, const void* R, int w, int h, int pitch, size_t plane, int max_pairs,
+                             int nslots, int th) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    if (!encode || w < 4 || h < 2) return false;
+    using C = FastBoxCfg<7, 24>;                                     // HALO / MH do not depend on the tile height
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, 5, (cuuint64_t)max_pairs};
+        const cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)plane * 2, (cuuint64_t)plane * 10};
+        const cuuint32_t box[4] = {(cuuint32_t)(kFbTW + 2 * C::HALO), (cuuint32_t)(th + 14), 5, 1};
+        if (encode(&out->m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(M), dims, strides, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    // R rows as chunks of 32 pixels (128 words = 512 B): a box row is one long burst, not a 16-byte pixel
+    if (pitch % 32 != 0) return false;
+    const cuuint64_t rdims[4] = {128, (cuuint64_t)(pitch / 32), (cuuint64_t)h, (cuuint64_t)nslots};
+    const cuuint64_t rstrides[3] = {512, (cuuint64_t)pitch * 16, (cuuint64_t)plane * 16};
+    const cuuint32_t box0[4] = {128, (cuuint32_t)(kFbTW / 32), (cuuint32_t)th, 1};
+    const cuuint32_t box1[4] = {128, (cuuint32_t)(kFbTW / 32 + 2), (cuuint32_t)(th + 4), 1};
+    if (encode(&out->r0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(R), rdims, rstrides, box0, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (encode(&out->r1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(R), rdims, rstrides, box1, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------------
