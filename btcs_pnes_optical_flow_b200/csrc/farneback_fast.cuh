@@ -85,17 +85,57 @@ struct TileMaps { CUtensorMap m, r0, r1; };
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
-// Vertical (2MH+1)-row box sums of one float4 column for kFbTH consecutive output rows; register ring window, software
-// prefetch 4 rows ahead.  ROWS_IN: the tile's rows (with halo) lie inside the image, `src` already points at the first
+// One row of a float4 column as it sits in the register window.  fp32 matrices: the float4 itself.  fp16 matrices: the
+// four raw halves (half the registers), consumed by the mixed-precision add of sm_100a (FHADD: f32 + f16 -> f32 in one
+// instruction, exact conversion included) so that no separate fp16 -> fp32 conversions are issued.
+__device__ __forceinline__ float fh_add(unsigned short h, float s) { float d; asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(s)); return d; }
+__device__ __forceinline__ float fh_sub(unsigned short h, float s) { float d; asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(s)); return d; }   // h - s
+struct HalfRow {
+    uint2 v;
+    __device__ __forceinline__ void split(unsigned short h[4]) const {
+        asm("mov.b32 {%0, %1}, %2;" : "=h"(h[0]), "=h"(h[1]) : "r"(v.x));
+        asm("mov.b32 {%0, %1}, %2;" : "=h"(h[2]), "=h"(h[3]) : "r"(v.y));
+    }
+};
+__device__ __forceinline__ float4 row_load(const float* p, float4*) { return m_load4(p); }
+__device__ __forceinline__ HalfRow row_load(const __half* p, HalfRow*) { return HalfRow{__ldg(reinterpret_cast<const uint2*>(p))}; }
+__device__ __forceinline__ float4 row_first(const float4& r) { return r; }
+__device__ __forceinline__ float4 row_first(const HalfRow& r) {
+    unsigned short h[4];
+    r.split(h);
+    return make_float4(fh_add(h[0], 0.f), fh_add(h[1], 0.f), fh_add(h[2], 0.f), fh_add(h[3], 0.f));
+}
+__device__ __forceinline__ void row_add(float4& s, const float4& r) { s = f4add(s, r); }
+__device__ __forceinline__ void row_add(float4& s, const HalfRow& r) {
+    unsigned short h[4];
+    r.split(h);
+    s.x = fh_add(h[0], s.x); s.y = fh_add(h[1], s.y); s.z = fh_add(h[2], s.z); s.w = fh_add(h[3], s.w);
+}
+// window slides one row: s += nv - ov
+__device__ __forceinline__ void row_slide(float4& s, const float4& nv, const float4& ov) { s = f4add(s, f4sub(nv, ov)); }
+__device__ __forceinline__ void row_slide(float4& s, const HalfRow& nv, const HalfRow& ov) {
+    unsigned short n[4], o[4];
+    nv.split(n); ov.split(o);
+    s.x = fh_sub(n[0], fh_sub(o[0], s.x));                   // nv - (ov - s)
+    s.y = fh_sub(n[1], fh_sub(o[1], s.y));
+    s.z = fh_sub(n[2], fh_sub(o[2], s.z));
+    s.w = fh_sub(n[3], fh_sub(o[3], s.w));
+}
+template <typename MT> struct RowOf { using type = float4; };
+template <> struct RowOf<__half> { using type = HalfRow; };
+
+// Vertical (2MH+1)-row box sums of one float4 column for TH consecutive output rows; register ring window, software
+// prefetch PF rows ahead.  ROWS_IN: the tile's rows (with halo) lie inside the image, `src` already points at the first
 // halo row.  Otherwise rows are clamped to [0, h-1] (replicate) starting from row `yb`.
 template <int MH, bool ROWS_IN, bool EDGE, int TH, int PF, typename MT>
 __device__ __forceinline__ void vertical_box_sums(const MT* __restrict__ src, unsigned pitch, int yb, int h, int mode,
                                                   float* __restrict__ dst, int vp) {
     constexpr int WIN = 2 * MH + 1, NROW = TH + 2 * MH;
-    auto ld = [&](int i) -> float4 {
-        if (ROWS_IN) return m_load4(src + (unsigned)i * pitch);
+    using Row = typename RowOf<MT>::type;
+    auto ld = [&](int i) -> Row {
+        if (ROWS_IN) return row_load(src + (unsigned)i * pitch, (Row*)nullptr);
         const int r = min(max(yb + i, 0), h - 1);
-        return m_load4(src + (unsigned)r * pitch);
+        return row_load(src + (unsigned)r * pitch, (Row*)nullptr);
     };
     auto st = [&](int j, const float4& s) {
         if (!EDGE) {                                      // compile-time: interior columns store the sums as they are
@@ -107,22 +147,22 @@ __device__ __forceinline__ void vertical_box_sums(const MT* __restrict__ src, un
             *reinterpret_cast<float4*>(dst + j * vp) = make_float4(e, e, e, e);
         }
     };
-    float4 win[WIN];
+    Row win[WIN];
 #pragma unroll
     for (int i = 0; i < WIN; ++i) win[i] = ld(i);
-    float4 s = win[0];
+    float4 s = row_first(win[0]);
 #pragma unroll
-    for (int i = 1; i < WIN; ++i) s = f4add(s, win[i]);
+    for (int i = 1; i < WIN; ++i) row_add(s, win[i]);
     st(0, s);
-    float4 pre[PF];
+    Row pre[PF];
 #pragma unroll
     for (int i = 0; i < PF; ++i) pre[i] = ld(WIN + i);
 #pragma unroll
     for (int j = 1; j < TH; ++j) {
-        const float4 nv = pre[(j - 1) % PF];
+        const Row nv = pre[(j - 1) % PF];
         if (j - 1 + PF + WIN < NROW) pre[(j - 1) % PF] = ld(WIN + j - 1 + PF);
-        const float4 ov = win[(j - 1) % WIN];
-        s = f4add(s, f4sub(nv, ov));
+        const Row ov = win[(j - 1) % WIN];
+        row_slide(s, nv, ov);
         win[(j - 1) % WIN] = nv;
         st(j, s);
     }
@@ -333,7 +373,11 @@ __global__ void __launch_bounds__(NW * 32, FastBoxCfg<MH, TH>::CTAS) k_blur_solv
         for (int j = 0; j < 4; ++j) {
             const float g11 = gs[0][j], g12 = gs[1][j], g22 = gs[2][j], h1 = gs[3][j], h2 = gs[4][j];
             const float det = diff_of_products(g11, g22, g12, g12) + reg;
-            const float idet = 1.f / det;
+            // det >= reg > 0 and far from the denormal range: compact plans take the 1-ulp hardware reciprocal (the IEEE
+            // division costs ~9 instructions per pixel); exact plans keep the division
+            float idet;
+            if (RH) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(idet) : "f"(det));
+            else idet = 1.f / det;
             fl[k][j].x = diff_of_products(g11, h2, g12, h1) * idet;
             fl[k][j].y = diff_of_products(g22, h1, g12, h2) * idet;
         }
@@ -618,12 +662,13 @@ inline bool blur_solve_fast_shape(int w, int h) { return (w % 4) == 0 && w >= 4 
 inline bool blur_solve_fast_aligned(const BlurSolveArgs& a) {
     return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0 && blur_solve_fast_shape(a.w, a.h);
 }
-// Tile height: 32 rows = 95 KB shared -> 2 CTAs/SM; 24 rows = 71 KB -> 3 CTAs/SM (default: the kernel is latency-bound,
-// more resident CTAs win over the extra vertical halo; measured in profiles/); 16 rows -> 4 CTAs/SM.
+// Tile height: 16 rows = 47 KB shared and 64 registers -> 4 CTAs/SM (default: the kernel is latency/issue-bound, resident
+// warps win over the extra vertical halo -- 1.26 ms per 64-pair 1080p launch against 1.48 at 24 rows / 3 CTAs and 1.50 at
+// 32 rows / 2 CTAs, profiles/).  64 registers hold only because the fp16 window of phase 1 stays packed (HalfRow).
 inline int tile_th() {
     const char* e = getenv("BTCSFLOW_TILE_TH");
-    const int v = e ? atoi(e) : 24;
-    return (v == 16 || v == 32) ? v : 24;
+    const int v = e ? atoi(e) : 16;
+    return (v == 24 || v == 32) ? v : 16;
 }
 inline int blur_solve_fast_ncta(int w, int h) { const int th = tile_th(); return ((w + kFbTW - 1) / kFbTW) * ((h + th - 1) / th); }
 
@@ -652,11 +697,12 @@ inline void launch_blur_solve_fast_t(const BlurSolveArgs& a, const WinCoef& wc, 
     const int th = tile_th();
     if (!RH || maps_th != th) maps = nullptr;
     switch (th) {
-        case 16: launch_blur_solve_fast_th<RH, 16>(a, wc, np, maps, st); break;
-        case 32: launch_blur_solve_fast_th<RH, 32>(a, wc, np, maps, st); break;
-        default:
+        case 24:
             if (tile_warps() == 6) launch_blur_solve_fast_th<RH, 24, 6>(a, wc, np, maps, st);
             else launch_blur_solve_fast_th<RH, 24>(a, wc, np, maps, st);
+            break;
+        case 32: launch_blur_solve_fast_th<RH, 32>(a, wc, np, maps, st); break;
+        default: launch_blur_solve_fast_th<RH, 16>(a, wc, np, maps, st);
     }
 }
 inline void launch_blur_solve_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st,
