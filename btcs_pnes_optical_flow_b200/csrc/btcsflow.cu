@@ -363,7 +363,7 @@ template <typename T>
 int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_bytes, int tf, int nf,
                   cudaStream_t st) {
     bool fused_l0 = false;
-    if (p->use_fast && p->W * (int)sizeof(float) * bf::kPyrRows <= 160 * 1024) {
+    if (p->use_fast && bf::pyr_h_smem_bytes(p->W) <= 160 * 1024) {
         // level 0: exact 3x3 stencil; coarser levels: one multi-level horizontal pass + per-level vertical pass
         bf::PyrHArgs pa{};
         // level 0 (scale 1): optionally fuse the blur into the polynomial expansion (BTCSFLOW_FUSED_L0=1).  Off by default:
@@ -383,7 +383,7 @@ int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_
                     continue;
                 }
                 dim3 g(cdiv(p->W, bf::kL0TW), cdiv(p->H, bf::kL0TH), nf);
-                bf::k_level0_blur<T><<<g, 256, 0, st>>>(frames, pitch_bytes, frame_bytes, p->W, p->H, s.I, s.pitch, s.plane);
+                bf::k_level0_blur<T><<<g, 128, 0, st>>>(frames, pitch_bytes, frame_bytes, p->W, p->H, s.I, s.pitch, s.plane);
                 LAUNCH_CHECK();
             } else if (pa.nlev < bf::kPyrMaxLevels) {
                 bf::PyrLevelDesc& d = pa.lv[pa.nlev++];
@@ -392,16 +392,22 @@ int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_
             }
         }
         if (pa.nlev > 0) {
-            const size_t smem = (size_t)(p->W + (p->W >> 5) + 1) * sizeof(float) * bf::kPyrRows;
+            const size_t smem = bf::pyr_h_smem_bytes(p->W);
             cudaFuncSetAttribute(bf::k_pyr_h_multi<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             bf::k_pyr_h_multi<T><<<dim3(cdiv(p->H, bf::kPyrRows), nf), 256, smem, st>>>(frames, pitch_bytes, frame_bytes, p->W,
                                                                                       p->H, pa);
             LAUNCH_CHECK();
             for (auto& s : p->sc) {
                 if (s.k == 0) continue;
-                dim3 b(64, 4), g2(cdiv(s.w, 64), cdiv(s.h, 4), nf);
-                bf::k_pyr_v<<<g2, b, 0, st>>>(s.tmpk, s.pitch, (size_t)p->H * s.pitch, p->H, s.w, s.h, s.iy, s.ay, s.kern,
-                                              s.ksize, s.I, s.pitch, s.plane);
+                if (bf::pyr_v4_ok(s.tmpk, s.pitch, (size_t)p->H * s.pitch, s.I, s.pitch, s.plane)) {
+                    dim3 b(32, 8), g2(cdiv(s.w, 128), cdiv(s.h, 8), nf);
+                    bf::k_pyr_v4<<<g2, b, 0, st>>>(s.tmpk, s.pitch, (size_t)p->H * s.pitch, p->H, s.w, s.h, s.iy, s.ay, s.kern,
+                                                   s.ksize, s.I, s.pitch, s.plane);
+                } else {
+                    dim3 b(64, 4), g2(cdiv(s.w, 64), cdiv(s.h, 4), nf);
+                    bf::k_pyr_v<<<g2, b, 0, st>>>(s.tmpk, s.pitch, (size_t)p->H * s.pitch, p->H, s.w, s.h, s.iy, s.ay, s.kern,
+                                                  s.ksize, s.I, s.pitch, s.plane);
+                }
                 LAUNCH_CHECK();
             }
         }

@@ -893,38 +893,63 @@ __global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I,
 // the result is bit-identical to cv2's row-then-column order).  Coarser levels: k_pyr_h_multi evaluates the horizontal
 // blur only at the columns the resize samples, for ALL coarser levels from one shared copy of each source row.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kL0TW = 128, kL0TH = 32;
+constexpr int kL0TW = 128, kL0TH = 32, kL0R = 8;          // tile of a 128-thread block; rows walked by one thread
 
+// One thread = 4 adjacent pixels x kL0R rows walking down: a row costs one 32-bit load (+ the two neighbour bytes), the
+// horizontally filtered rows slide through registers, every output row is one 128-bit store.  ~12 instructions per pixel;
+// the shared-tile version it replaces spent 78 (index arithmetic and reflection tests per loaded element; ncu, profiles/).
 template <typename T>
-__global__ void __launch_bounds__(256) k_level0_blur(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes,
+__global__ void __launch_bounds__(128) k_level0_blur(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes,
                                                      int W, int H, float* __restrict__ out, int out_pitch,
                                                      size_t out_frame_stride) {
-    __shared__ float t[kL0TH + 2][kL0TW + 4];
-    const int x0 = blockIdx.x * kL0TW, y0 = blockIdx.y * kL0TH, f = blockIdx.z;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x = (blockIdx.x * 32 + lane) * 4;
+    const int yb = blockIdx.y * kL0TH + wid * kL0R;
+    const int f = blockIdx.z;
+    if (x >= W || yb >= H) return;
     const char* base = (const char*)src + (size_t)f * src_frame_bytes;
-    for (int e = threadIdx.x; e < (kL0TH + 2) * (kL0TW + 2); e += 256) {
-        const int ry = e / (kL0TW + 2), rx = e - ry * (kL0TW + 2);
-        const int gy = reflect101(min(y0 + ry - 1, H), H), gx = reflect101(min(x0 + rx - 1, W), W);
-        t[ry][rx] = load_px((const T*)(base + (size_t)gy * src_pitch_bytes) + gx);
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, rb = threadIdx.x >> 5;
+    float* obase = out + (size_t)f * out_frame_stride;
+    // interior threads of aligned uint8 frames fetch their 4 pixels as one word
+    const bool word = sizeof(T) == 1 && x >= 1 && x + 4 < W &&
+                      ((src_pitch_bytes | src_frame_bytes | reinterpret_cast<uintptr_t>(src)) & 3) == 0;
+    const bool vec_out = x + 3 < W && (out_pitch & 3) == 0 && (out_frame_stride & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    auto hrow = [&](int yy, float hr[4]) {                                    // row filter first, like cv2
+        const T* row = (const T*)(base + (size_t)reflect101(min(yy, H), H) * src_pitch_bytes);
+        float v[6];
+        if (word) {
+            const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(row + x));
+            v[0] = load_px(row + x - 1);
+            v[1] = (float)q.x; v[2] = (float)q.y; v[3] = (float)q.z; v[4] = (float)q.w;
+            v[5] = load_px(row + x + 4);
+        } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int r = rb + 8 * k, y = y0 + r;
-        if (y >= H) continue;
-        float* orow = out + (size_t)f * out_frame_stride + (size_t)y * out_pitch;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int cx = lane + 32 * j, x = x0 + cx;                       // lanes on consecutive pixels: no bank conflicts
-            float hr[3];
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const float* q = &t[r + dy][cx];
-                hr[dy] = q[0] * 0.25f + q[1] * 0.5f + q[2] * 0.25f;          // row filter first, like cv2
-            }
-            if (x < W) orow[x] = hr[0] * 0.25f + hr[1] * 0.5f + hr[2] * 0.25f;
+            for (int i = 0; i < 6; ++i) v[i] = load_px(row + reflect101(min(x - 1 + i, W), W));
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hr[j] = v[j] * 0.25f + v[j + 1] * 0.5f + v[j + 2] * 0.25f;
+    };
+    float h0[4], h1[4], h2[4];
+    hrow(yb - 1, h0);
+    hrow(yb, h1);
+#pragma unroll
+    for (int k = 0; k < kL0R; ++k) {
+        const int y = yb + k;
+        if (y >= H) break;
+        hrow(y + 1, h2);
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = h0[j] * 0.25f + h1[j] * 0.5f + h2[j] * 0.25f;
+        float* op = obase + (size_t)y * out_pitch + x;
+        if (vec_out) {
+            *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j < W) op[j] = o[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { h0[j] = h1[j]; h1[j] = h2[j]; }
     }
 }
 
@@ -1041,83 +1066,136 @@ struct PyrLevelDesc {
 constexpr int kPyrMaxLevels = 15;
 struct PyrHArgs { PyrLevelDesc lv[kPyrMaxLevels]; int nlev; };
 
-// One CTA per (kPyrRows source rows, frame): the rows are converted to float in shared memory once (128-bit loads for
-// uint8) and every coarser level takes its horizontally blurred + column-interpolated samples from them; the tap tables
-// (ix, ax, kernel) are read once per output column and applied to all kPyrRows rows.
+// One CTA per (kPyrRows = 4 source rows, frame).  The four rows are converted to float once and kept INTERLEAVED in
+// shared memory -- one float4 per source pixel holding the 4 rows, pixel i in slot i + (i >> 3) -- so a tap is one
+// LDS.128 for all rows, conflict-free for the power-of-two lane strides of the decimating levels (lanes 1, 2, 4, 8 source
+// pixels apart land in 8 distinct 16-byte bank groups per quarter warp).  Every coarser level takes its horizontally
+// blurred + column-interpolated samples from that copy; tap tables are read once per output column.  (The planar layout
+// this replaces spent 83 instructions per source pixel, mostly shared-memory index arithmetic; ncu, profiles/.)
 constexpr int kPyrRows = 4;
+__host__ __device__ inline int pyr_slot(int i) { return i + (i >> 3); }
+inline size_t pyr_h_smem_bytes(int W) { return (size_t)(pyr_slot(W) + 1) * sizeof(float4); }
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes,
                                                      int W, int H, const PyrHArgs pa) {
-    // [kPyrRows][WP], element i of a row lives at i + (i >> 5): one pad word per 32 makes the power-of-two strides of the
-    // decimating levels (lanes 2, 4, 8 ... source pixels apart) bank-conflict free
-    extern __shared__ __align__(16) float srow[];
-    const int WP = W + (W >> 5) + 1;
-    auto sx = [](int i) { return i + (i >> 5); };
+    extern __shared__ __align__(16) float4 srow4[];
     const int r0 = blockIdx.x * kPyrRows, f = blockIdx.y;
     const char* fbase = (const char*)src + (size_t)f * src_frame_bytes;
-    const bool vec = (sizeof(T) == 1) && ((W & 15) == 0) && ((src_pitch_bytes & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(fbase) & 15) == 0);
-    for (int rr = 0; rr < kPyrRows; ++rr) {
-        const int r = min(r0 + rr, H - 1);
-        const T* row = (const T*)(fbase + (size_t)r * src_pitch_bytes);
-        float* dstrow = srow + rr * WP;
-        if (vec) {
-            for (int x = threadIdx.x * 16; x < W; x += 256 * 16) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(row) + x));
-                const unsigned wds[4] = {u.x, u.y, u.z, u.w};
+    const T* rows[kPyrRows];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+    for (int rr = 0; rr < kPyrRows; ++rr) rows[rr] = (const T*)(fbase + (size_t)min(r0 + rr, H - 1) * src_pitch_bytes);
+    const bool vec = (sizeof(T) == 1) && ((W & 3) == 0) && ((src_pitch_bytes & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(fbase) & 3) == 0);
+    if (vec) {
+        for (int x = threadIdx.x * 4; x < W; x += 256 * 4) {
+            unsigned q[kPyrRows];
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) dstrow[sx(x + 4 * k + b)] = (float)((wds[k] >> (8 * b)) & 0xffu);
-            }
-        } else {
-            for (int x = threadIdx.x; x < W; x += 256) dstrow[sx(x)] = load_px(row + x);
+            for (int rr = 0; rr < kPyrRows; ++rr) q[rr] = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const uint8_t*>(rows[rr]) + x));
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                srow4[pyr_slot(x + b)] = make_float4((float)((q[0] >> (8 * b)) & 0xffu), (float)((q[1] >> (8 * b)) & 0xffu),
+                                                     (float)((q[2] >> (8 * b)) & 0xffu), (float)((q[3] >> (8 * b)) & 0xffu));
         }
+    } else {
+        for (int x = threadIdx.x; x < W; x += 256)
+            srow4[pyr_slot(x)] = make_float4(load_px(rows[0] + x), load_px(rows[1] + x), load_px(rows[2] + x), load_px(rows[3] + x));
     }
     __syncthreads();
     for (int l = 0; l < pa.nlev; ++l) {
         const PyrLevelDesc& d = pa.lv[l];
-        const int rad = d.ksize >> 1;
+        const int rad = d.ksize >> 1, ksize = d.ksize;
+        const float* __restrict__ kern = d.kern;
         float* tbase = d.tmp + (size_t)f * d.tmp_frame_stride + (size_t)r0 * d.tmp_pitch;
         for (int x = threadIdx.x; x < d.w; x += 256) {
             const int i0 = d.ix[x];
             const float a = d.ax[x];
-            float b0[kPyrRows], b1[kPyrRows];
-#pragma unroll
-            for (int rr = 0; rr < kPyrRows; ++rr) b0[rr] = b1[rr] = 0.f;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
             if (i0 - rad >= 0 && i0 + 1 + rad < W) {
-                float prev[kPyrRows];
-#pragma unroll
-                for (int rr = 0; rr < kPyrRows; ++rr) prev[rr] = srow[rr * WP + sx(i0 - rad)];
-                for (int j = 0; j < d.ksize; ++j) {
-                    const float kj = __ldg(d.kern + j);
-                    const int cn = sx(i0 - rad + j + 1);
-#pragma unroll
-                    for (int rr = 0; rr < kPyrRows; ++rr) {
-                        const float nxt = srow[rr * WP + cn];
-                        b0[rr] = fmaf(kj, prev[rr], b0[rr]);
-                        b1[rr] = fmaf(kj, nxt, b1[rr]);
-                        prev[rr] = nxt;
-                    }
+                int i = i0 - rad;
+                float4 prev = srow4[pyr_slot(i)];
+                for (int j = 0; j < ksize; ++j) {
+                    const float kj = __ldg(kern + j);
+                    ++i;
+                    const float4 nxt = srow4[pyr_slot(i)];
+                    b0.x = fmaf(kj, prev.x, b0.x); b0.y = fmaf(kj, prev.y, b0.y); b0.z = fmaf(kj, prev.z, b0.z); b0.w = fmaf(kj, prev.w, b0.w);
+                    b1.x = fmaf(kj, nxt.x, b1.x); b1.y = fmaf(kj, nxt.y, b1.y); b1.z = fmaf(kj, nxt.z, b1.z); b1.w = fmaf(kj, nxt.w, b1.w);
+                    prev = nxt;
                 }
             } else {
                 const int i1 = min(i0 + 1, W - 1);
-                for (int j = 0; j < d.ksize; ++j) {
-                    const float kj = __ldg(d.kern + j);
-                    const int c0 = sx(reflect101(i0 - rad + j, W)), c1 = sx(reflect101(i1 - rad + j, W));
-#pragma unroll
-                    for (int rr = 0; rr < kPyrRows; ++rr) {
-                        b0[rr] = fmaf(kj, srow[rr * WP + c0], b0[rr]);
-                        b1[rr] = fmaf(kj, srow[rr * WP + c1], b1[rr]);
-                    }
+                for (int j = 0; j < ksize; ++j) {
+                    const float kj = __ldg(kern + j);
+                    const float4 v0 = srow4[pyr_slot(reflect101(i0 - rad + j, W))], v1 = srow4[pyr_slot(reflect101(i1 - rad + j, W))];
+                    b0.x = fmaf(kj, v0.x, b0.x); b0.y = fmaf(kj, v0.y, b0.y); b0.z = fmaf(kj, v0.z, b0.z); b0.w = fmaf(kj, v0.w, b0.w);
+                    b1.x = fmaf(kj, v1.x, b1.x); b1.y = fmaf(kj, v1.y, b1.y); b1.z = fmaf(kj, v1.z, b1.z); b1.w = fmaf(kj, v1.w, b1.w);
                 }
             }
+            const float o[kPyrRows] = {(a != 0.f) ? (b0.x * (1.f - a) + b1.x * a) : b0.x, (a != 0.f) ? (b0.y * (1.f - a) + b1.y * a) : b0.y,
+                                       (a != 0.f) ? (b0.z * (1.f - a) + b1.z * a) : b0.z, (a != 0.f) ? (b0.w * (1.f - a) + b1.w * a) : b0.w};
 #pragma unroll
             for (int rr = 0; rr < kPyrRows; ++rr)
-                if (r0 + rr < H) tbase[(size_t)rr * d.tmp_pitch + x] = (a != 0.f) ? (b0[rr] * (1.f - a) + b1[rr] * a) : b0[rr];
+                if (r0 + rr < H) tbase[(size_t)rr * d.tmp_pitch + x] = o[rr];
         }
     }
+}
+
+// Vertical part, 4 adjacent columns per thread (128-bit loads of the horizontal-pass rows, 128-bit store): out[f][y][x] =
+// lerp_y(blur_v(tmp)).  Same arithmetic as k_pyr_v (farneback_kernels.cuh), which remains for unaligned pitches.
+__global__ void __launch_bounds__(256) k_pyr_v4(const float* __restrict__ tmp, int tmp_pitch, size_t tmp_frame_stride, int H, int w,
+                                                int h, const int* __restrict__ iy, const float* __restrict__ ay,
+                                                const float* __restrict__ kern, int ksize, float* __restrict__ out, int out_pitch,
+                                                size_t out_frame_stride) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.z;
+    if (x >= w || y >= h) return;
+    const float* t = tmp + (size_t)f * tmp_frame_stride + x;
+    const int rad = ksize >> 1;
+    const int i0 = iy[y];
+    const float a = ay[y];
+    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    auto ldrow = [&](int r) { return __ldg(reinterpret_cast<const float4*>(t + (size_t)r * tmp_pitch)); };
+    if (i0 - rad >= 0 && i0 + 1 + rad < H) {
+        const float* q = t + (size_t)(i0 - rad) * tmp_pitch;
+        float4 prev = __ldg(reinterpret_cast<const float4*>(q));
+        for (int j = 0; j < ksize; ++j) {
+            q += tmp_pitch;
+            const float4 nxt = __ldg(reinterpret_cast<const float4*>(q));
+            const float kj = __ldg(kern + j);
+            b0.x = fmaf(kj, prev.x, b0.x); b0.y = fmaf(kj, prev.y, b0.y); b0.z = fmaf(kj, prev.z, b0.z); b0.w = fmaf(kj, prev.w, b0.w);
+            b1.x = fmaf(kj, nxt.x, b1.x); b1.y = fmaf(kj, nxt.y, b1.y); b1.z = fmaf(kj, nxt.z, b1.z); b1.w = fmaf(kj, nxt.w, b1.w);
+            prev = nxt;
+        }
+    } else {
+        for (int j = 0; j < ksize; ++j) {
+            const float kj = __ldg(kern + j);
+            const float4 v = ldrow(reflect101(i0 - rad + j, H));
+            b0.x = fmaf(kj, v.x, b0.x); b0.y = fmaf(kj, v.y, b0.y); b0.z = fmaf(kj, v.z, b0.z); b0.w = fmaf(kj, v.w, b0.w);
+        }
+        if (a != 0.f) {
+            const int i1 = min(i0 + 1, H - 1);
+            for (int j = 0; j < ksize; ++j) {
+                const float kj = __ldg(kern + j);
+                const float4 v = ldrow(reflect101(i1 - rad + j, H));
+                b1.x = fmaf(kj, v.x, b1.x); b1.y = fmaf(kj, v.y, b1.y); b1.z = fmaf(kj, v.z, b1.z); b1.w = fmaf(kj, v.w, b1.w);
+            }
+        }
+    }
+    float4 v = b0;
+    if (a != 0.f) v = make_float4(b0.x * (1.f - a) + b1.x * a, b0.y * (1.f - a) + b1.y * a, b0.z * (1.f - a) + b1.z * a, b0.w * (1.f - a) + b1.w * a);
+    float* op = out + (size_t)f * out_frame_stride + (size_t)y * out_pitch + x;
+    if (x + 3 < w) {
+        *reinterpret_cast<float4*>(op) = v;
+    } else {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < 4 && x + j < w; ++j) op[j] = vv[j];
+    }
+}
+// pitches and bases that allow the 128-bit version (plan buffers always do: pitch is a multiple of 32 floats)
+inline bool pyr_v4_ok(const void* tmp, int tmp_pitch, size_t tmp_frame_stride, const void* out, int out_pitch, size_t out_frame_stride) {
+    return aligned16(tmp) && aligned16(out) && (tmp_pitch % 4) == 0 && (out_pitch % 4) == 0 && (tmp_frame_stride % 4) == 0 &&
+           (out_frame_stride % 4) == 0;
 }
 
 inline bool polyexp_fast_supported(int n, int pitch) { return (n == 5 || n == 7) && (pitch % 4) == 0; }

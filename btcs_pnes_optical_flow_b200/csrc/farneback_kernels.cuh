@@ -476,25 +476,40 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     const bool inner = (x >= 5) && (x < w - 5) && (yb >= 5) && (yb + kUpdRows <= h - 5);
     // flow_init of the thread's rows first (independent loads), then the updates
     float2 fl[kUpdRows];
+    if (a.flow_mode == 2) {
+        // bilinear sample of the coarser flow (cv2.resize INTER_LINEAR) times mult.  The rows of a warp are
+        // uniform, and consecutive fine rows share coarse rows (4 fine rows touch 4 coarse rows at pyr_scale 0.5, not 8):
+        // the x-interpolated coarse rows are carried from one fine row to the next.
+        const float ub = 1.f - ua;
+        auto hrow = [&](int yc) -> float2 {
+            const unsigned r = (unsigned)yc * (unsigned)a.flow_pitch;
+            const float2 p0 = fin[r + (unsigned)ux0], p1 = fin[r + (unsigned)ux1];
+            return make_float2(p0.x * ub + p1.x * ua, p0.y * ub + p1.y * ua);
+        };
+        int c0 = -1, c1 = -1;
+        float2 H0 = make_float2(0.f, 0.f), H1 = H0;
 #pragma unroll
-    for (int k = 0; k < kUpdRows; ++k) {
-        const int y = min(yb + k, h - 1);
-        fl[k] = make_float2(0.f, 0.f);
-        if (a.flow_mode == 1) {
-            fl[k] = fin[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x];
-        } else if (a.flow_mode == 2) {
-            // bilinear sample of the coarser flow (cv2.resize INTER_LINEAR) times mult
+        for (int k = 0; k < kUpdRows; ++k) {
+            const int y = min(yb + k, h - 1);
             const int y0 = a.tab.iy[y], y1 = min(y0 + 1, a.hs - 1);
             const float b = a.tab.ay[y];
-            const unsigned r0 = (unsigned)y0 * (unsigned)a.flow_pitch, r1 = (unsigned)y1 * (unsigned)a.flow_pitch;
-            const float2 p00 = fin[r0 + (unsigned)ux0], p01 = fin[r0 + (unsigned)ux1];
-            const float2 p10 = fin[r1 + (unsigned)ux0], p11 = fin[r1 + (unsigned)ux1];
-            const float h0x = p00.x * (1.f - ua) + p01.x * ua, h0y = p00.y * (1.f - ua) + p01.y * ua;
-            const float h1x = p10.x * (1.f - ua) + p11.x * ua, h1y = p10.y * (1.f - ua) + p11.y * ua;
-            fl[k].x = (h0x * (1.f - b) + h1x * b) * a.mult;
-            fl[k].y = (h0y * (1.f - b) + h1y * b) * a.mult;
+            const float2 h0 = (y0 == c0) ? H0 : ((y0 == c1) ? H1 : hrow(y0));
+            const float2 h1 = (y1 == y0) ? h0 : ((y1 == c1) ? H1 : ((y1 == c0) ? H0 : hrow(y1)));
+            c0 = y0; H0 = h0; c1 = y1; H1 = h1;
+            fl[k].x = (h0.x * (1.f - b) + h1.x * b) * a.mult;
+            fl[k].y = (h0.y * (1.f - b) + h1.y * b) * a.mult;
         }
-        if (fout && yb + k < h) fout[(unsigned)y * (unsigned)a.flow_out_pitch + (unsigned)x] = fl[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < kUpdRows; ++k) {
+            const int y = min(yb + k, h - 1);
+            fl[k] = a.flow_mode == 1 ? fin[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x] : make_float2(0.f, 0.f);
+        }
+    }
+    if (fout) {
+#pragma unroll
+        for (int k = 0; k < kUpdRows; ++k)
+            if (yb + k < h) fout[(unsigned)(yb + k) * (unsigned)a.flow_out_pitch + (unsigned)x] = fl[k];
     }
     if (!Mo) return;
     if (RH && w >= 2 && h >= 2) {
