@@ -880,11 +880,12 @@ int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* 
         LAUNCH_CHECK();
         roi.masks = p->d_masks; roi.n_roi = n_roi; roi.ex = p->d_ex; roi.ey = p->d_ey; roi.out = p->d_out; roi.T = T;
     }
-    // Chunks of up to B pairs, double-buffered: chunk c+1 travels on the copy stream while chunk c computes.  The first
-    // chunk is kept short so that compute starts after ~8 frames have arrived instead of after a full B+1-frame chunk.
+    // Chunks of up to B pairs, double-buffered: chunk c+1 travels on the copy stream while chunk c computes.  The chunks
+    // grow 8 -> 24 -> B: compute starts after ~8 frames have arrived, and since a pair takes ~3.5x longer to compute than a
+    // frame takes to cross PCIe, each chunk's copy is hidden behind the previous (3x smaller) chunk's compute.
     int chunk = 0;
     for (int t0 = 0; t0 < T - 1; ++chunk) {
-        const int cap = (chunk == 0) ? std::min(p->B, 8) : p->B;
+        const int cap = (chunk == 0) ? std::min(p->B, 8) : (chunk == 1 ? std::min(p->B, 24) : p->B);
         const int np = std::min(cap, T - 1 - t0);
         const int tf = (t0 == 0) ? 0 : t0 + 1;
         const int nf = t0 + np - tf + 1;

@@ -766,9 +766,12 @@ inline bool encode_tile_maps(TileMaps* out, const void* M, const void* R, int w,
 // ---------------------------------------------------------------------------------------------------
 template <int N>
 struct FastPeCfg {
-    static constexpr int HALO = (N + 3) / 4 * 4;
+    // HALO = N exactly: a 4-output group then reads the 2N + 4 values it needs from float4 chunk 0 onwards, all of them
+    // LDS.128.  With the halo rounded up to 8 the first and last value sat alone in their chunks and were fetched by scalar
+    // LDS with a 16-byte lane stride (4-way bank conflicts, a quarter of the kernel's shared-memory wavefronts; ncu).
+    static constexpr int HALO = N;
     static constexpr int NCOL = kFbTW + 2 * HALO;
-    static constexpr int VP = NCOL + 4;
+    static constexpr int VP = (NCOL + 3) / 4 * 4 + 4;
     static constexpr int RG = 4, RPG = kFbTH / RG;             // row groups, rows per group
     static constexpr int NCH = (HALO + N + 3) / 4 + 1;
     static constexpr size_t SMEM = (size_t)3 * kFbTH * VP * sizeof(float);
@@ -849,7 +852,7 @@ __device__ __forceinline__ void polyexp_horizontal_store(const float* smem, int 
 }
 
 template <int N, bool RH>
-__global__ void __launch_bounds__(256, 2) k_polyexp(const float* __restrict__ I, int pitch, size_t frame_stride, int w,
+__global__ void __launch_bounds__(256, 4) k_polyexp(const float* __restrict__ I, int pitch, size_t frame_stride, int w,
                                                     int h, void* __restrict__ Rv, size_t plane_stride,
                                                     size_t slot_stride, int slot0, int nslots, const PolyCoef pc) {
     using C = FastPeCfg<N>;
