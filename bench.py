@@ -283,7 +283,7 @@ def run_ours(args, spec, params):
             tpi = measured_traffic_per_pair_iteration()
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": (tpi * prof["pair_iterations"] / prof["launches"]) if tpi else None,
-                    "kernel": "k_blur_solve_box<7,RH,24>: blur+solve(+update) at the finest scale",
+                    "kernel": "k_blur_solve_box<7,RH,%s>: blur+solve(+update) at the finest scale" % (os.environ.get("BTCSFLOW_TILE_TH") or "16"),
                     "launches": prof["launches"], "avg_launch_ms": prof["total_ms"] / prof["launches"],
                     "algorithmic_bytes_per_launch": prof["pair_iterations"] * bytes_per_pair_iter / prof["launches"],
                     "kernel_share_of_step": prof["total_ms"] / ms_total, "peak_source": peak_src,
