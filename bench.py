@@ -204,7 +204,7 @@ def run_ours(args, spec, params):
         if not full.is_cuda:
             full = full.to(dev)
         s = full[0].double()
-        return pca.flow_to_pc1(None, s[:, 0].contiguous(), s[:, 1].contiguous(), fs_hz=spec.fps).cpu().numpy()
+        return pca.flow_to_pc1(None, s[:, 0].contiguous(), s[:, 1].contiguous(), fs_hz=spec.fps, sos=sos).cpu().numpy()
 
     def launch_device():
         """Asynchronous part of a step: flow -> ROI series on the device, gather to rank 0 (NCCL)."""

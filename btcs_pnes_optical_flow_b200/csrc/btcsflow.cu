@@ -853,6 +853,33 @@ int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* 
         if ((rc = plan_alloc(p, &p->stage_flow, (size_t)p->B * fb * 2))) return rc;
     }
     RoiCtx roi;
+    // Chunks of up to B pairs, double-buffered: chunk c+1 travels on the copy stream while chunk c computes.  The chunks
+    // grow 8 -> 24 -> B: compute starts after ~8 frames have arrived, and since a pair takes ~3.5x longer to compute than a
+    // frame takes to cross PCIe, each chunk's copy is hidden behind the previous (3x smaller) chunk's compute.
+    int ramp[4] = {8, 24, 0, 0};                       // BTCSFLOW_HOST_CHUNKS="a,b,..." overrides the ramp (experiments)
+    if (const char* e = getenv("BTCSFLOW_HOST_CHUNKS")) {
+        int k = 0;
+        ramp[0] = ramp[1] = 0;
+        for (const char* q = e; *q && k < 4; ++k) {
+            ramp[k] = atoi(q);
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+    }
+    auto chunk_cap = [&](int chunk) { return (chunk < 4 && ramp[chunk] > 0) ? std::min(p->B, ramp[chunk]) : p->B; };
+    auto issue_copy = [&](int chunk, int t0) -> int {          // frames of chunk `chunk` (pairs t0 .. t0+np-1) -> staging
+        const int np = std::min(chunk_cap(chunk), T - 1 - t0);
+        const int tf = (t0 == 0) ? 0 : t0 + 1;
+        const int nf = t0 + np - tf + 1;
+        const int b = chunk & 1;
+        if (chunk >= 2) CU(cudaStreamWaitEvent(p->copy_stream, p->ev_free[b], 0));
+        CU(cudaMemcpyAsync(p->stage[b], frames + (size_t)tf * fb, (size_t)nf * fb, cudaMemcpyHostToDevice, p->copy_stream));
+        CU(cudaEventRecord(p->ev_copied[b], p->copy_stream));
+        return 0;
+    };
+    // The first chunk's frames are queued on the copy stream BEFORE the ROI masks and axes go up: those come from pageable
+    // memory (staged, synchronous copies, ~0.3 ms for a 1080p mask) and would otherwise delay the first frame.
+    if (T > 1 && (rc = issue_copy(0, 0))) return rc;
     if (n_roi > 0) {
         if (p->axes_cap < T) {
             cudaFree(p->d_ex); cudaFree(p->d_ey); p->d_ex = p->d_ey = nullptr;
@@ -880,19 +907,14 @@ int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* 
         LAUNCH_CHECK();
         roi.masks = p->d_masks; roi.n_roi = n_roi; roi.ex = p->d_ex; roi.ey = p->d_ey; roi.out = p->d_out; roi.T = T;
     }
-    // Chunks of up to B pairs, double-buffered: chunk c+1 travels on the copy stream while chunk c computes.  The chunks
-    // grow 8 -> 24 -> B: compute starts after ~8 frames have arrived, and since a pair takes ~3.5x longer to compute than a
-    // frame takes to cross PCIe, each chunk's copy is hidden behind the previous (3x smaller) chunk's compute.
     int chunk = 0;
     for (int t0 = 0; t0 < T - 1; ++chunk) {
-        const int cap = (chunk == 0) ? std::min(p->B, 8) : (chunk == 1 ? std::min(p->B, 24) : p->B);
-        const int np = std::min(cap, T - 1 - t0);
+        const int np = std::min(chunk_cap(chunk), T - 1 - t0);
         const int tf = (t0 == 0) ? 0 : t0 + 1;
         const int nf = t0 + np - tf + 1;
         const int b = chunk & 1;
-        if (chunk >= 2) CU(cudaStreamWaitEvent(p->copy_stream, p->ev_free[b], 0));
-        CU(cudaMemcpyAsync(p->stage[b], frames + (size_t)tf * fb, (size_t)nf * fb, cudaMemcpyHostToDevice, p->copy_stream));
-        CU(cudaEventRecord(p->ev_copied[b], p->copy_stream));
+        // the NEXT chunk's copy is queued before this chunk's ~45 launches so that the copy stream stays a chunk ahead
+        if (t0 + np < T - 1 && (rc = issue_copy(chunk + 1, t0 + np))) return rc;
         CU(cudaStreamWaitEvent(st, p->ev_copied[b], 0));
         rc = expand_frames<uint8_t>(p, p->stage[b], (size_t)p->W, fb, tf, nf, st);
         if (rc) return rc;

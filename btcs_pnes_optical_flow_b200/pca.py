@@ -150,12 +150,14 @@ def sosfilt_zi(sos: np.ndarray) -> np.ndarray:
 
 def flow_to_pc1(t, vx, vy, fs_hz: float = fs, win_sec: float = WIN_SEC, step_sec: float = STEP_SEC,
                 low_hz: float = BPF_LOW_HZ, high_hz: float = BPF_HIGH_HZ, order: int = BPF_ORDER,
-                on_device: bool = True):
+                on_device: bool = True, sos: np.ndarray | None = None):
     """Band-pass + dynamic PC1 for one series: the body of optical_PCA.main (optical_PCA.py:254-267).
 
     on_device=True (default) runs the band-pass on the GPU too, so a torch CUDA series never leaves the device;
-    on_device=False uses scipy on the host for the band-pass exactly like the reference."""
-    sos = butter_bandpass_sos(low_hz, high_hz, fs_hz, order=order)
+    on_device=False uses scipy on the host for the band-pass exactly like the reference.  `sos`: a filter already designed
+    with butter_bandpass_sos (the design costs ~0.4 ms of host time; streaming callers design it once)."""
+    if sos is None:
+        sos = butter_bandpass_sos(low_hz, high_hz, fs_hz, order=order)
     if on_device:
         import torch
         is_torch = type(vx).__module__.startswith("torch")

@@ -33,3 +33,10 @@ def finish():
 print(f"PC1 tail (series H2D, band-pass, PCA, PC1 D2H): {tm(finish):.2f} ms")
 for first in (None,):
     pass
+import os
+for ramp in ("8,24", "64", "8", "16", "16,48", "4,12,36", "32"):
+    os.environ["BTCSFLOW_HOST_CHUNKS"] = ramp
+    print(f"host-buffer series call, chunk ramp {ramp:8s}: {tm(lambda: plan.flow_series(frames_host, None, None, mask_host), 7):.2f} ms")
+os.environ.pop("BTCSFLOW_HOST_CHUNKS")
+# how long do the pieces of the host path take when nothing overlaps?
+t0 = time.perf_counter(); m = torch.from_numpy(mask_host).to(dev); torch.cuda.synchronize(); print(f"mask H2D: {1e3 * (time.perf_counter() - t0):.2f} ms")
