@@ -571,7 +571,10 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_gauss(const BlurSolveArgs
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float g11 = gs[0][j], g12 = gs[1][j], g22 = gs[2][j], h1 = gs[3][j], h2 = gs[4][j];
-            const float idet = 1.f / (diff_of_products(g11, g22, g12, g12) + 1e-3f);
+            const float det = diff_of_products(g11, g22, g12, g12) + 1e-3f;
+            float idet;
+            if (RH) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(idet) : "f"(det));      // see k_blur_solve_box
+            else idet = 1.f / det;
             fl[k][j].x = diff_of_products(g11, h2, g12, h1) * idet;
             fl[k][j].y = diff_of_products(g22, h1, g12, h2) * idet;
         }
@@ -587,12 +590,21 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_gauss(const BlurSolveArgs
 
     // ---------------- phase 3: coalesced tail (same as the box kernel) ----------------
     const int lane = tid & 31, wid = tid >> 5;
+    // a warp walks down one 32-pixel column group (4 column groups x 2 row halves), see k_blur_solve_box
+    const int tail_r0 = (wid >> 2) * (4 * C::RG), tail_c0 = (wid & 3) * 32 + lane;
+    auto tail_row = [&](int i) { return tail_r0 + i; };
+    auto tail_col = [&](int) { return tail_c0; };
     if (a.flow || a.Mout) {
         float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
         MT* Mo = a.Mout ? static_cast<MT*>(a.Mout) + (size_t)p * a.m_stride : nullptr;
+        const bool inner = (x0 >= 5) && (y0 >= 5) && (x0 + kFbTW <= w - 5) && (y0 + TH <= h - 5);
+        if (RH && Mo && !fo && w >= 2 && h >= 2) {
+            if (inner) update_tail_pipelined<false, C::RG>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, plane, pitch, w, h, x0, y0, tail_row, tail_col);
+            else update_tail_pipelined<true, C::RG>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, plane, pitch, w, h, x0, y0, tail_row, tail_col);
+        } else
 #pragma unroll 4
         for (int i = 0; i < 4 * C::RG; ++i) {
-            const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
+            const int r = tail_row(i), cx = tail_col(i);
             const int x = x0 + cx, y = y0 + r;
             if (x < w && y < h) {
                 const float2 f = F[r * kFbTW + cx];
@@ -614,7 +626,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_gauss(const BlurSolveArgs
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 4
             for (int i = 0; i < 4 * C::RG; ++i) {
-                const int r = wid * C::RG + (i >> 2), cx = (i & 3) * 32 + lane;
+                const int r = tail_row(i), cx = tail_col(i);
                 const int x = x0 + cx, y = y0 + r;
                 if (x < w && y < h && mk[(size_t)y * a.mask_pitch + x] != 0) {
                     const float2 f = F[r * kFbTW + cx];

@@ -139,6 +139,9 @@ def test_all_kernel_variants_agree(monkeypatch):
                               ("tile_f32", {"BTCSFLOW_R_STORAGE": "f32"}),
                               ("march_f32", {"BTCSFLOW_KERNEL": "march", "BTCSFLOW_R_STORAGE": "f32"}),
                               ("fused_l0", {"BTCSFLOW_FUSED_L0": "1"}),
+                              ("no_tmap", {"BTCSFLOW_TMAP": "0"}),            # per-row L2 prefetch instead of tensor maps
+                              ("serial_tail", {"BTCSFLOW_TAIL": "serial"}),   # gathers not issued ahead
+                              ("th24", {"BTCSFLOW_TILE_TH": "24"}), ("th32", {"BTCSFLOW_TILE_TH": "32"}),
                               ("generic", {"BTCSFLOW_NO_FAST": "1"})):
                 for k, v in env.items():
                     monkeypatch.setenv(k, v)
@@ -152,6 +155,10 @@ def test_all_kernel_variants_agree(monkeypatch):
             # compact storage (fp16 R and M): both kernels quantise the same values, summation order differs
             assert epe(outs["march"], outs["generic"])[1] < 2e-3 and epe(outs["tile"], outs["march"])[1] < 1e-3
             assert epe(outs["fused_l0"], outs["tile"])[1] < 1e-3        # level-0 blur fused into the expansion (opt-in)
+            # prefetch flavour and gather scheduling do not touch the arithmetic; tile height only moves where the
+            # running vertical sums restart
+            assert np.array_equal(outs["no_tmap"], outs["tile"]) and np.array_equal(outs["serial_tail"], outs["tile"])
+            assert epe(outs["th24"], outs["tile"])[1] < 1e-3 and epe(outs["th32"], outs["tile"])[1] < 1e-3
 
 
 def test_1080p_full_size_properties():
