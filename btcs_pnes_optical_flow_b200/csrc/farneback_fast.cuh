@@ -2,16 +2,17 @@
 //
 // k_blur_solve_box<MH>: flow = Solve(BoxBlur_{2MH+1}(M)) fused with M' = UpdateMatrices(flow) and/or the
 // body-axis projection + ROI partial sums (reference call site optical_flow.py:173, reduction
-// optical_flow.py:176-187).  One CTA = 128 x 32 output pixels, 256 threads, 2 CTAs per SM.
-//   phase 1  vertical window sums, global -> shared.  One thread per (channel, float4 column): 128-bit coalesced
-//            loads, the 2MH+1 row window lives in registers (fully unrolled ring), exact first window then
-//            add-new/subtract-old with a history bounded by the 32+2MH rows of the tile: no long-range
-//            cancellation, and all-zero (static) regions stay exactly zero.
+// optical_flow.py:176-187).  One CTA = 128 x TH output pixels (TH = 16 by default), 256 threads, 4 CTAs per SM.
+//   phase 0  three tensor-map prefetches (UTMAPF) bring the M tile and the R0 / R1 blocks of the tile into L2.
+//   phase 1  vertical window sums, global -> shared.  One thread per (channel, 4-column group): 64-bit (fp16 M) or 128-bit
+//            coalesced loads, the 2MH+1 row window lives in registers (fully unrolled ring; raw fp16 rows consumed by
+//            FHADD on compact plans), exact first window then add-new/subtract-old with a history bounded by the TH+2MH
+//            rows of the tile: no long-range cancellation, and all-zero (static) regions stay exactly zero.
 //   phase 2  horizontal window sums from shared with conflict-free LDS.128 (lane stride 16 B), 4 outputs per
 //            thread sharing the common partial sum (no subtraction), then the 2x2 solve with Kahan-accurate
 //            determinants.  The 1/winsize^2 scale is folded into the regulariser (reg = 1e-3 * winsize^4).
 //   phase 3  flow is transposed through shared memory so that lanes own consecutive pixels again: coalesced R0
-//            loads, bilinear R1 gather, M' stores; ROI sums reduced per CTA (deterministic partials).
+//            loads, bilinear R1 gather issued one pixel ahead, M' stores; ROI sums reduced per CTA (deterministic partials).
 #pragma once
 #include <cstdlib>
 #include <cstring>
