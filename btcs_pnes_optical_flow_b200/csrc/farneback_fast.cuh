@@ -128,8 +128,10 @@ template <> struct RowOf<__half> { using type = HalfRow; };
 // Vertical (2MH+1)-row box sums of one float4 column for TH consecutive output rows; register ring window, software
 // prefetch PF rows ahead.  ROWS_IN: the tile's rows (with halo) lie inside the image, `src` already points at the first
 // halo row.  Otherwise rows are clamped to [0, h-1] (replicate) starting from row `yb`.
+// mode (EDGE only): 0 = group inside the image, 1 = left of it (splat lane 0 of the first group), 2 = right of it (splat
+// lane kl of the last group), 3 = the last group of an image whose width is not a multiple of 4 (lanes above kl take lane kl).
 template <int MH, bool ROWS_IN, bool EDGE, int TH, int PF, typename MT>
-__device__ __forceinline__ void vertical_box_sums(const MT* __restrict__ src, unsigned pitch, int yb, int h, int mode,
+__device__ __forceinline__ void vertical_box_sums(const MT* __restrict__ src, unsigned pitch, int yb, int h, int mode, int kl,
                                                   float* __restrict__ dst, int vp) {
     constexpr int WIN = 2 * MH + 1, NROW = TH + 2 * MH;
     using Row = typename RowOf<MT>::type;
@@ -144,8 +146,9 @@ __device__ __forceinline__ void vertical_box_sums(const MT* __restrict__ src, un
         } else if (mode == 0) {
             *reinterpret_cast<float4*>(dst + j * vp) = s;
         } else {
-            const float e = mode == 1 ? s.x : s.w;
-            *reinterpret_cast<float4*>(dst + j * vp) = make_float4(e, e, e, e);
+            const float e = (mode == 1 || kl == 0) ? s.x : (kl == 1 ? s.y : (kl == 2 ? s.z : s.w));
+            const bool keep = mode == 3;
+            *reinterpret_cast<float4*>(dst + j * vp) = make_float4(keep ? s.x : e, (keep && kl >= 1) ? s.y : e, (keep && kl >= 2) ? s.z : e, e);
         }
     };
     Row win[WIN];
@@ -322,21 +325,22 @@ __global__ void __launch_bounds__(NW * 32, FastBoxCfg<MH, TH>::CTAS) k_blur_solv
 
     BF_TRACE_STAMP(1);
     // ---------------- phase 1: vertical sums ----------------
-    // w % 4 == 0 and float4-aligned columns: a float4 column is entirely inside the image, entirely left of it or
-    // entirely right of it.  Outside columns load the nearest inside chunk and splat its edge lane when the SUM is
+    // 4-column groups are aligned to the image origin: a group is entirely inside the image, entirely left of it, entirely
+    // right of it, or (width not a multiple of 4) the one group that straddles the right edge.  Outside columns load the nearest inside chunk and splat its edge lane when the SUM is
     // stored (replicate border; splat commutes with the sum), so the load path is branch-free.
     const bool rows_in = (y0 - MH >= 0) && (y0 + TH + MH <= h);      // block-uniform: no row clamping needed
     for (int task = tid; task < 5 * C::NC4; task += NT) {
         const int c = task / C::NC4, q = task - c * C::NC4;
         const int gx = x0 - C::HALO + 4 * q;
-        const int mode = gx < 0 ? 1 : (gx >= w ? 2 : 0);
-        const int cgx = mode == 1 ? 0 : (mode == 2 ? w - 4 : gx);
+        const int wl = (w - 1) & ~3, kl = (w - 1) & 3;                // last group that holds a pixel, and that pixel's lane
+        const int mode = gx < 0 ? 1 : (gx > wl ? 2 : ((gx == wl && kl != 3) ? 3 : 0));
+        const int cgx = mode == 1 ? 0 : (mode == 2 ? wl : gx);
         const MT* src = Mp + (size_t)c * plane + (unsigned)cgx;
         float* dst = V + (size_t)c * TH * C::VP + 4 * q;
         // four instantiations: rows inside / clamped x interior column / replicated edge column (edge columns are rare
         // and were costing 7.5 FSEL per pixel when handled by selects)
-        if (mode == 0 && rows_in) vertical_box_sums<MH, true, false, TH, C::PF>(src + (unsigned)(y0 - MH) * pitch, pitch, 0, 0, 0, dst, C::VP);
-        else vertical_box_sums<MH, false, true, TH, C::PF>(src, pitch, y0 - MH, h, mode, dst, C::VP);
+        if (mode == 0 && rows_in) vertical_box_sums<MH, true, false, TH, C::PF>(src + (unsigned)(y0 - MH) * pitch, pitch, 0, 0, 0, 0, dst, C::VP);
+        else vertical_box_sums<MH, false, true, TH, C::PF>(src, pitch, y0 - MH, h, mode, kl, dst, C::VP);
     }
     __syncthreads();
     BF_TRACE_STAMP(2);
@@ -670,8 +674,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline bool blur_solve_fast_supported(const WinCoef& wc, int pitch) {
     return !wc.gauss && wc.m == 7 && (pitch % 4) == 0;
 }
-// + the image width must be a multiple of 4 (float4 columns are all-inside or all-outside) and at least one chunk
-inline bool blur_solve_fast_shape(int w, int h) { return (w % 4) == 0 && w >= 4 && h >= 2; }
+// + at least one 4-column group and two rows (the clamped gather footprint); the row pitch (a multiple of 4 elements,
+// checked above) covers the last group when the width is not a multiple of 4
+inline bool blur_solve_fast_shape(int w, int h) { return w >= 4 && h >= 2; }
 inline bool blur_solve_fast_aligned(const BlurSolveArgs& a) {
     return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0 && blur_solve_fast_shape(a.w, a.h);
 }

@@ -286,7 +286,7 @@ inline void march_plan(int w, int h, int np, int sm_count, int& nstrip, int& nse
 }
 
 inline bool march_supported(const WinCoef& wc, const BlurSolveArgs& a) {
-    return !wc.gauss && wc.m == 7 && blur_solve_fast_aligned(a) && (a.pitch % 4) == 0 &&
+    return !wc.gauss && wc.m == 7 && blur_solve_fast_aligned(a) && (a.pitch % 4) == 0 && (a.w % 4) == 0 &&
            (!a.partial || a.n_roi <= kMarchMaxRoi);
 }
 

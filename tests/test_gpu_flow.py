@@ -161,6 +161,25 @@ def test_all_kernel_variants_agree(monkeypatch):
             assert epe(outs["th24"], outs["tile"])[1] < 1e-3 and epe(outs["th32"], outs["tile"])[1] < 1e-3
 
 
+def test_widths_not_multiple_of_4(monkeypatch):
+    """The tile kernel's last 4-column group may straddle the right edge (replicate border inside the group): widths with
+    every residue mod 4, against cv2 and against the runtime-parameter kernel."""
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    for w in (317, 318, 319, 133):
+        a, b = textured(150, w, w), textured(150, w, w, shift=(1.3, 0.6))
+        ref = cv2_ref.farneback(a, b, **B.FB_PARAMS)
+        with B.FlowPlan(w, 150, B.FB_PARAMS) as plan:
+            got = plan.flow_pair(a, b)
+        monkeypatch.setenv("BTCSFLOW_NO_FAST", "1")
+        with B.FlowPlan(w, 150, B.FB_PARAMS) as plan:
+            gen = plan.flow_pair(a, b)
+        monkeypatch.delenv("BTCSFLOW_NO_FAST")
+        mean, inner, band = epe_banded(got, ref, 16)
+        assert mean <= MEAN_TIGHT and inner <= MAX_TIGHT and band <= 0.25, (w, mean, inner, band)
+        assert epe(got, gen)[1] < 5e-3, (w, epe(got, gen))          # compact vs fp32 storage, same border handling
+
+
 def test_1080p_full_size_properties():
     """BASELINE full size: parity on one pair + size-independent properties (translation recovery, determinism)."""
     import btcs_pnes_optical_flow_b200 as B

@@ -41,13 +41,13 @@ for case in range(n_cases):
             mean, inner, edge = epe_banded(got, ref, band)
         # compact plans: a fifth of the north_star gates on the interior (narrow Gaussian windows average less: up to 5e-3)
         ok = mean <= 1e-3 and inner <= 1e-2 and edge <= 0.25 and np.isfinite(got).all()
-        if exact: ok = ok and edge <= 5e-3
+        if exact: ok = ok and inner <= 1e-4           # fp32 storage: ~1e-6 inside; the band can still hold a branch flip (rounding order)
         worst.append((inner, edge, mean, case, h, w, exact, p))
         if not ok:
             bad += 1
             print("GATE BROKEN", case, h, w, "exact" if exact else "compact", p, "mean %.2e inner %.2e band %.2e" % (mean, inner, edge))
     # series row 1 = ROI mean of the pair's flow (identity axes) over the interior (the border band may hold branch flips)
-    want = ref[inner_mask != 0].mean(0)
+    want = ref[inner_mask != 0].mean(0, dtype=np.float64)   # float64: a float32 column-wise mean of 1e5 same-sign values drifts by ~1e-3
     if not (np.isnan(ser[0]).all() and np.abs(ser[1, :2] - want).max() < 5e-4):
         bad += 1
         print("SERIES MISMATCH", case, h, w, p, ser[1], want)
