@@ -327,10 +327,10 @@ BlurKernel choose_blur_kernel(const bf::BlurSolveArgs& a, const bf::WinCoef& wc,
     return BK_GENERIC;
 }
 
-int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast) {
+int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast, bool r_half) {
     switch (choose_blur_kernel(a, wc, allow_fast)) {
         case BK_MARCH: return bf::march_ncta(a.w, a.h, np, sm_count_cached());
-        case BK_TILE: return bf::blur_solve_fast_ncta(a.w, a.h);
+        case BK_TILE: return bf::blur_solve_fast_ncta(a.w, a.h, r_half);
         case BK_GAUSS: return bf::gauss_fast_ncta(a.w, a.h);
         default: return cdiv(a.w, bf::kBsTW) * cdiv(a.h, bf::kBsTH);
     }
@@ -523,7 +523,7 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
                 p->prof_pairs += np;
             }
             if (last && finest && want_roi) {
-                const int ncta = blur_solve_ncta(a, p->wc, np, p->use_fast);
+                const int ncta = blur_solve_ncta(a, p->wc, np, p->use_fast, p->r_half);
                 bf::k_roi_finalize<<<cdiv(np * roi->n_roi, 4), 128, 0, st>>>(p->partial, np, roi->n_roi, ncta, roi->ex,
                                                                              roi->ey, t0 + 1, roi->out, roi->T);
                 LAUNCH_CHECK();
@@ -670,7 +670,7 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
     {
         const char* e = getenv("BTCSFLOW_TMAP");
         if (p->r_half && p->use_fast && !(e && e[0] == '0')) {
-            const int th = bf::tile_th();
+            const int th = bf::tile_th(true);
             for (auto& s : p->sc) {
                 if (!bf::blur_solve_fast_shape(s.w, s.h)) continue;
                 if (bf::encode_tile_maps(&s.maps[0], p->M[0], s.R, s.w, s.h, s.pitch, s.plane, p->B, p->F, th) &&

@@ -680,15 +680,20 @@ inline bool blur_solve_fast_shape(int w, int h) { return w >= 4 && h >= 2; }
 inline bool blur_solve_fast_aligned(const BlurSolveArgs& a) {
     return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 4) == 0 && blur_solve_fast_shape(a.w, a.h);
 }
-// Tile height: 16 rows = 47 KB shared and 64 registers -> 4 CTAs/SM (default: the kernel is latency/issue-bound, resident
-// warps win over the extra vertical halo -- 1.26 ms per 64-pair 1080p launch against 1.48 at 24 rows / 3 CTAs and 1.50 at
-// 32 rows / 2 CTAs, profiles/).  64 registers hold only because the fp16 window of phase 1 stays packed (HalfRow).
-inline int tile_th() {
+// Tile height.  Compact plans: 16 rows = 47 KB shared and 64 registers -> 4 CTAs/SM (the kernel is latency/issue-bound,
+// resident warps win over the extra vertical halo -- 1.26 ms per 64-pair 1080p launch against 1.48 at 24 rows / 3 CTAs and
+// 1.50 at 32 rows / 2 CTAs, profiles/); 64 registers hold only because the fp16 window of phase 1 stays packed (HalfRow).
+// Exact plans (float4 window rows, 60 registers of window alone): 32 rows / 128 registers without spills is fastest
+// (2.40 ms against 2.52 / 2.55 at 24 / 16 rows).  BTCSFLOW_TILE_TH overrides both.
+inline int tile_th(bool r_half) {
     const char* e = getenv("BTCSFLOW_TILE_TH");
-    const int v = e ? atoi(e) : 16;
-    return (v == 24 || v == 32) ? v : 16;
+    const int v = e ? atoi(e) : (r_half ? 16 : 32);
+    return (v == 16 || v == 24 || v == 32) ? v : (r_half ? 16 : 32);
 }
-inline int blur_solve_fast_ncta(int w, int h) { const int th = tile_th(); return ((w + kFbTW - 1) / kFbTW) * ((h + th - 1) / th); }
+inline int blur_solve_fast_ncta(int w, int h, bool r_half) {
+    const int th = tile_th(r_half);
+    return ((w + kFbTW - 1) / kFbTW) * ((h + th - 1) / th);
+}
 
 inline bool tail_pipelined() {
     const char* e = getenv("BTCSFLOW_TAIL");
@@ -712,7 +717,7 @@ inline void launch_blur_solve_fast_th(const BlurSolveArgs& a, const WinCoef& wc,
 template <bool RH>
 inline void launch_blur_solve_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, const TileMaps* maps, int maps_th,
                                      cudaStream_t st) {
-    const int th = tile_th();
+    const int th = tile_th(RH);
     if (!RH || maps_th != th) maps = nullptr;
     switch (th) {
         case 24:
