@@ -199,31 +199,54 @@ def run_ours(args, spec, params):
     plan = B.FlowPlan(spec.W, spec.H, params, max_pairs=args.max_pairs, max_rois=1, device=local_rank)
     sos = pca.butter_bandpass_sos(pca.BPF_LOW_HZ, pca.BPF_HIGH_HZ, spec.fps)
 
-    def finish(full):
+    side = torch.cuda.Stream(device=dev)        # the PC1 tail runs beside the next step's flow kernels, not behind them
+
+    def finish(full, ready=None):
         """rank 0: series -> band-pass -> sliding PCA -> PC1, all on the GPU; only the PC1 waveform comes back."""
-        if not full.is_cuda:
-            full = full.to(dev)
-        s = full[0].double()
-        return pca.flow_to_pc1(None, s[:, 0].contiguous(), s[:, 1].contiguous(), fs_hz=spec.fps, sos=sos).cpu().numpy()
+        if ready is not None:
+            side.wait_event(ready)
+        with torch.cuda.stream(side):
+            if not full.is_cuda:
+                full = full.to(dev)
+            else:
+                full.record_stream(side)
+            s = full[0].double()
+            return pca.flow_to_pc1(None, s[:, 0].contiguous(), s[:, 1].contiguous(), fs_hz=spec.fps, sos=sos).cpu().numpy()
 
     def launch_device():
         """Asynchronous part of a step: flow -> ROI series on the device, gather to rank 0 (NCCL)."""
         series = plan.flow_series(frames_dev, None, None, mask_dev)            # [1, P+1, 3] on the device
-        return D.gather_series(series[:, 1:], rows, T_total)
+        full = D.gather_series(series[:, 1:], rows, T_total)
+        ready = torch.cuda.Event()
+        ready.record()
+        return full, ready
 
     def step_device():
-        full = launch_device()
+        return tail_device(launch_device())
+
+    def launch_host():
+        """Streaming host-buffer call: pinned frames in, queued H2D chunks + compute, series D2H; returns a handle."""
+        return plan.flow_series_async(frames_host, None, None, mask_host)
+
+    def tail_host(handle):
+        series = handle.result()                                               # this step's series has reached the host
+        if world > 1:
+            with torch.cuda.stream(side):                                      # the gather must not queue behind the next step
+                full = D.gather_series(torch.from_numpy(series[:, 1:]).to(dev), rows, T_total)
+        else:
+            full = torch.from_numpy(series)
         return finish(full) if rank == 0 else None
 
     def step_host():
-        series = plan.flow_series(frames_host, None, None, mask_host)          # host buffers: H2D/D2H inside
-        full = D.gather_series(torch.from_numpy(series[:, 1:]).to(dev), rows, T_total) if world > 1 else \
-            torch.from_numpy(series)
-        return finish(full) if rank == 0 else None
+        return tail_host(launch_host())
 
-    def timed(fn, steps, warmup, profile=False, launch=None):
-        """launch=None: fn() per step.  With `launch`, the host-side tail of step i (series D2H, band-pass, PC1) runs
-        after step i+1 has been queued, as a streaming caller would do it; the work per step is the same."""
+    def tail_device(launched):
+        full, ready = launched
+        return finish(full, ready) if rank == 0 else None
+
+    def timed(fn, steps, warmup, profile=False, launch=None, tail=None):
+        """launch=None: fn() per step.  With `launch` + `tail`, the tail of step i (series gather, band-pass, PC1, D2H)
+        runs after step i+1 has been queued, as a streaming caller would do it; the work per step is the same."""
         for _ in range(warmup):
             fn()
         if world > 1:
@@ -242,11 +265,10 @@ def run_ours(args, spec, params):
             pending = None
             for _ in range(steps):
                 nxt = launch()
-                if pending is not None and rank == 0:
-                    out = finish(pending)
+                if pending is not None:
+                    out = tail(pending)
                 pending = nxt
-            if rank == 0:
-                out = finish(pending)
+            out = tail(pending)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -262,9 +284,11 @@ def run_ours(args, spec, params):
         return float(ms.item()), launches, prof, out
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_total, launches, prof, pc1 = timed(step_device, args.steps, args.warmup, profile=True, launch=launch_device)
+    ms_total, launches, prof, pc1 = timed(step_device, args.steps, args.warmup, profile=True, launch=launch_device,
+                                          tail=tail_device)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _, _, pc1_h = timed(step_host, args.steps, max(1, args.warmup // 2) if args.warmup else 0)
+    ms_e2e, _, _, pc1_h = timed(step_host, args.steps, max(1, args.warmup // 2) if args.warmup else 0, launch=launch_host,
+                                tail=tail_host)
 
     if rank == 0:
         pairs = world * P * args.steps

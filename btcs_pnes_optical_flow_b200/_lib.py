@@ -58,6 +58,8 @@ _SIGNATURES = {
     "bf_flow_pair_host": (_i, [_vp, _vp, _vp, _i, _sz, _vp, _vp]),
     "bf_flow_series": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "bf_flow_series_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "bf_flow_series_host_async": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, C.POINTER(C.c_longlong)]),
+    "bf_flow_series_wait": (_i, [_vp, C.c_longlong]),
     "bf_pc1_sliding": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _vp]),
     "bf_pc1_sliding_batched": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp]),
     "bf_pc1_sliding_host": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _i, _vp]),

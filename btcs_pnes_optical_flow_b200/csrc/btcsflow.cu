@@ -221,6 +221,10 @@ struct bf_plan {
     float* d_out = nullptr; size_t out_cap = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    bool ev_free_rec[2] = {false, false};       // staging buffer b has a pending "expansion done" event (also across calls)
+    static constexpr int kTickets = 8;
+    cudaEvent_t ev_done[kTickets] = {};         // completion events of bf_flow_series_host_async calls (ring)
+    long long next_ticket = 0;
     bool use_fast = true;
     bool r_half = false;        // polynomial coefficients packed in 16 B per pixel, b f32 + A f16 (fast path, uint8 input)
     int sm_count = 148;
@@ -704,6 +708,7 @@ int bf_plan_destroy(bf_plan* p) {
         if (p->ev_copied[i]) cudaEventDestroy(p->ev_copied[i]);
         if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]);
     }
+    for (auto ev : p->ev_done) if (ev) cudaEventDestroy(ev);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     for (auto ev : p->prof_ev) cudaEventDestroy(ev);
     delete p;
@@ -830,10 +835,12 @@ int bf_flow_series(bf_plan* p, const uint8_t* frames, int T, const double* ex, c
     return 0;
 }
 
-int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* ex, const double* ey,
-                        const uint8_t* roi_masks, int n_roi, float* out, float* flow_out, void* stream) {
+int bf_flow_series_host_async(bf_plan* p, const uint8_t* frames, int T, const double* ex, const double* ey,
+                              const uint8_t* roi_masks, int n_roi, float* out, float* flow_out, void* stream,
+                              long long* ticket) {
     int rc = check_plan(p);
     if (rc) return rc;
+    if (!ticket) return fail(BF_E_INVALID, "ticket is NULL");
     if (T < 1 || !frames) return fail(BF_E_INVALID, "need frames and T >= 1");
     if (n_roi < 0 || n_roi > p->max_rois) return fail(BF_E_INVALID, "n_roi=%d exceeds plan max_rois=%d", n_roi, p->max_rois);
     if (n_roi > 0 && (!roi_masks || !out || !ex || !ey)) return fail(BF_E_INVALID, "ROI reduction needs masks, axes and out");
@@ -872,7 +879,9 @@ int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* 
         const int tf = (t0 == 0) ? 0 : t0 + 1;
         const int nf = t0 + np - tf + 1;
         const int b = chunk & 1;
-        if (chunk >= 2) CU(cudaStreamWaitEvent(p->copy_stream, p->ev_free[b], 0));
+        // the staging buffer must have been consumed by the expansion of the chunk that used it last (this call's chunk - 2,
+        // or the tail of an earlier asynchronous call)
+        if (p->ev_free_rec[b]) CU(cudaStreamWaitEvent(p->copy_stream, p->ev_free[b], 0));
         CU(cudaMemcpyAsync(p->stage[b], frames + (size_t)tf * fb, (size_t)nf * fb, cudaMemcpyHostToDevice, p->copy_stream));
         CU(cudaEventRecord(p->ev_copied[b], p->copy_stream));
         return 0;
@@ -919,6 +928,7 @@ int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* 
         rc = expand_frames<uint8_t>(p, p->stage[b], (size_t)p->W, fb, tf, nf, st);
         if (rc) return rc;
         CU(cudaEventRecord(p->ev_free[b], st));
+        p->ev_free_rec[b] = true;
         rc = run_pairs(p, t0, np, flow_out ? p->stage_flow : nullptr, n_roi > 0 ? &roi : nullptr, st);
         if (rc) return rc;
         if (flow_out)
@@ -928,7 +938,30 @@ int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* 
     }
     if (n_roi > 0)
         CU(cudaMemcpyAsync(out, p->d_out, (size_t)n_roi * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    const int slot = (int)(p->next_ticket % bf_plan::kTickets);
+    if (!p->ev_done[slot]) CU(cudaEventCreateWithFlags(&p->ev_done[slot], cudaEventDisableTiming));
+    CU(cudaEventRecord(p->ev_done[slot], st));
+    *ticket = p->next_ticket++;
+    return 0;
+}
+
+int bf_flow_series_wait(bf_plan* p, long long ticket) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    if (ticket < 0 || ticket >= p->next_ticket) return fail(BF_E_INVALID, "unknown ticket %lld", ticket);
+    // if the slot was reused by a later call, that call was queued behind this one: waiting for it is sufficient
+    DeviceGuard dg(p->device);
+    CU(cudaEventSynchronize(p->ev_done[ticket % bf_plan::kTickets]));
+    return 0;
+}
+
+int bf_flow_series_host(bf_plan* p, const uint8_t* frames, int T, const double* ex, const double* ey,
+                        const uint8_t* roi_masks, int n_roi, float* out, float* flow_out, void* stream) {
+    long long ticket = -1;
+    int rc = bf_flow_series_host_async(p, frames, T, ex, ey, roi_masks, n_roi, out, flow_out, stream, &ticket);
+    if (rc) return rc;
+    DeviceGuard dg(p->device);
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
     CU(cudaStreamSynchronize(p->copy_stream));
     return 0;
 }

@@ -217,6 +217,28 @@ class FlowPlan:
             out[:] = np.nan
         return (out, flow) if return_flow else out
 
+    def flow_series_async(self, frames, ex=None, ey=None, roi_masks=None):
+        """Streaming form of flow_series for host frames: queues the call and returns a PendingSeries at once;
+        `.result()` blocks until that call has finished and returns the float32 [n_roi, T, 3] series (a view of pinned
+        memory owned by the pending object).  Calls on one plan run in submission order, so a caller walking a list of
+        recordings can submit clip k+1 before consuming clip k.  `frames` should be pinned (e.g. torch `pin_memory()`)."""
+        import ctypes as C
+        import torch
+        frames = np.ascontiguousarray(frames)
+        if frames.dtype != np.uint8 or frames.ndim != 3 or frames.shape[1:] != (self.height, self.width):
+            raise Cv2CompatError(-1, f"frames must be uint8 [T, {self.height}, {self.width}]")
+        T = frames.shape[0]
+        ex, ey = _axes(ex, ey, T)
+        masks = _masks(roi_masks, self.height, self.width)
+        if masks.shape[0] > self.max_rois:
+            raise Cv2CompatError(-1, f"{masks.shape[0]} ROI masks > plan max_rois={self.max_rois}")
+        out_t = torch.empty((masks.shape[0], T, 3), dtype=torch.float32, pin_memory=True)
+        ticket = C.c_longlong(-1)
+        check(self._lib.bf_flow_series_host_async(self._h, frames.ctypes.data, T, ex.ctypes.data, ey.ctypes.data,
+                                                  masks.ctypes.data, masks.shape[0], out_t.data_ptr(), None,
+                                                  _current_stream_ptr(self.device), C.byref(ticket)))
+        return PendingSeries(self, int(ticket.value), out_t, frames, T)
+
     def _flow_series_torch(self, frames, ex, ey, roi_masks, return_flow):
         import torch
         if not frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() != 3 \
@@ -248,6 +270,23 @@ class FlowPlan:
         for t in (frames, ex_t, ey_t, masks):
             t.record_stream(torch.cuda.current_stream(dev))
         return (out, flow) if return_flow else out
+
+
+class PendingSeries:
+    """Handle of one FlowPlan.flow_series_async call (keeps the frames and the pinned result buffer alive)."""
+
+    def __init__(self, plan, ticket, out_t, frames, T):
+        self._plan, self._ticket, self._out, self._frames, self._T = plan, ticket, out_t, frames, T
+        self._done = False
+
+    def result(self) -> np.ndarray:
+        if not self._done:
+            check(self._plan._lib.bf_flow_series_wait(self._plan._h, self._ticket))
+            self._done = True
+            self._frames = None
+            if self._T == 1:
+                self._out.fill_(float("nan"))
+        return self._out.numpy()
 
 
 def _coerce_pair(prev, nxt, W: int | None = None, H: int | None = None):

@@ -119,6 +119,15 @@ int bf_flow_series(bf_plan* plan, const uint8_t* frames, int T, const double* ex
  * back and the call returns after everything has completed.  flow_out (host) optional. */
 int bf_flow_series_host(bf_plan* plan, const uint8_t* frames, int T, const double* ex, const double* ey,
                         const uint8_t* roi_masks, int n_roi, float* out, float* flow_out, void* stream);
+/* Streaming form of the same call (a caller walking a list of clips, optical_flow.py:195-259 called per recording): returns
+ * once the work is queued and hands back a ticket; bf_flow_series_wait(ticket) blocks until that call's `out` / `flow_out`
+ * are complete.  Calls on one plan execute in submission order; frames, out and flow_out must stay valid until the wait
+ * and should be pinned (pageable buffers make the copies -- and hence the call -- synchronous).  ex, ey and roi_masks are
+ * consumed before the call returns.  At most 8 tickets are tracked; waiting on an older one waits for a newer call. */
+int bf_flow_series_host_async(bf_plan* plan, const uint8_t* frames, int T, const double* ex, const double* ey,
+                              const uint8_t* roi_masks, int n_roi, float* out, float* flow_out, void* stream,
+                              long long* ticket);
+int bf_flow_series_wait(bf_plan* plan, long long ticket);
 
 /* ---- sliding-window PCA -> PC1 (replaces dynamic_pc1_sliding, optical_PCA.py:136-235) ---------------- */
 

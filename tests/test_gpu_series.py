@@ -131,3 +131,23 @@ def test_bgr_to_gray_bit_exact():
         assert got.dtype == np.uint8 and np.array_equal(got, ref)
     dev = B.bgr_to_gray(torch.from_numpy(x).cuda())
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), ref)
+
+
+def test_async_host_series_matches_sync():
+    """flow_series_async: two clips in flight on one plan, results equal to the synchronous host call."""
+    import torch
+    import btcs_pnes_optical_flow_b200 as B
+    from btcs_pnes_optical_flow_b200 import synthetic as syn
+    spec = syn.ClipSpec(T=21, H=135, W=240, seed=3, patch=60, roi=80, amp=3.0)
+    a = syn.make_clip_np(spec)
+    b = np.ascontiguousarray(a[::-1])
+    pa, pb = torch.from_numpy(a).pin_memory().numpy(), torch.from_numpy(b).pin_memory().numpy()
+    mask = spec.roi_mask()
+    with B.FlowPlan(spec.W, spec.H, B.FB_PARAMS, max_pairs=4, max_rois=1) as plan:
+        want_a, want_b = plan.flow_series(a, None, None, mask), plan.flow_series(b, None, None, mask)
+        ha = plan.flow_series_async(pa, None, None, mask)
+        hb = plan.flow_series_async(pb, None, None, mask)        # queued behind the first, staging buffers shared
+        got_b, got_a = hb.result().copy(), ha.result().copy()
+        one = plan.flow_series_async(pa[:1], None, None, mask).result()
+    assert np.array_equal(got_a, want_a, equal_nan=True) and np.array_equal(got_b, want_b, equal_nan=True)
+    assert one.shape == (1, 1, 3) and np.isnan(one).all()
