@@ -499,7 +499,7 @@ struct FastGaussCfg {
 };
 
 template <int MH, bool RH, int TH>
-__global__ void __launch_bounds__(256, 2) k_blur_solve_gauss(const BlurSolveArgs a, const WinCoef wc) {
+__global__ void __launch_bounds__(256, TH >= 32 ? 2 : (TH >= 24 ? 3 : 4)) k_blur_solve_gauss(const BlurSolveArgs a, const WinCoef wc) {
     using C = FastGaussCfg<MH, TH>;
     using MT = typename MStore<RH>::type;
     extern __shared__ __align__(16) float smem[];
@@ -654,19 +654,31 @@ __global__ void __launch_bounds__(256, 2) k_blur_solve_gauss(const BlurSolveArgs
     }
 }
 
-constexpr int kGaussTH = 32;
+inline int gauss_th() {
+    const char* e = getenv("BTCSFLOW_GAUSS_TH");
+    const int v = e ? atoi(e) : 24;
+    return (v == 16 || v == 32) ? v : 24;
+}
 inline bool gauss_fast_supported(const WinCoef& wc) { return wc.gauss && wc.m == 10; }
-inline int gauss_fast_ncta(int w, int h) { return ((w + kFbTW - 1) / kFbTW) * ((h + kGaussTH - 1) / kGaussTH); }
-template <bool RH>
+inline int gauss_fast_ncta(int w, int h) { const int th = gauss_th(); return ((w + kFbTW - 1) / kFbTW) * ((h + th - 1) / th); }
+template <bool RH, int TH>
 inline void launch_gauss_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
-    using C = FastGaussCfg<10, kGaussTH>;
-    cudaFuncSetAttribute(k_blur_solve_gauss<10, RH, kGaussTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    dim3 g((a.w + kFbTW - 1) / kFbTW, (a.h + kGaussTH - 1) / kGaussTH, np);
-    k_blur_solve_gauss<10, RH, kGaussTH><<<g, 256, C::SMEM, st>>>(a, wc);
+    using C = FastGaussCfg<10, TH>;
+    cudaFuncSetAttribute(k_blur_solve_gauss<10, RH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    dim3 g((a.w + kFbTW - 1) / kFbTW, (a.h + TH - 1) / TH, np);
+    k_blur_solve_gauss<10, RH, TH><<<g, 256, C::SMEM, st>>>(a, wc);
 }
 inline void launch_gauss_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st) {
-    if (r_half) launch_gauss_fast_t<true>(a, wc, np, st);
-    else launch_gauss_fast_t<false>(a, wc, np, st);
+    const int th = gauss_th();
+    if (r_half) {
+        if (th == 16) launch_gauss_fast_t<true, 16>(a, wc, np, st);
+        else if (th == 32) launch_gauss_fast_t<true, 32>(a, wc, np, st);
+        else launch_gauss_fast_t<true, 24>(a, wc, np, st);
+    } else {
+        if (th == 16) launch_gauss_fast_t<false, 16>(a, wc, np, st);
+        else if (th == 32) launch_gauss_fast_t<false, 32>(a, wc, np, st);
+        else launch_gauss_fast_t<false, 24>(a, wc, np, st);
+    }
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
