@@ -1,6 +1,6 @@
 """Randomised parity sweep against cv2 on the GPU box: ragged sizes and parameter sets through flow_pair (compact and exact
 plans) and through the series path.  Prints the worst cases; exits non-zero if a gate is broken.
-usage: python tools/fuzz_parity.py [n_cases] [seed]"""
+usage: python tools/fuzz_parity.py [n_cases] [seed] [MAXWxMAXH]"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -11,10 +11,11 @@ from tests.helpers import textured, epe_banded
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+max_h, max_w = (int(v) for v in (sys.argv[3].split("x")[::-1] if len(sys.argv) > 3 else ("420", "520")))
 worst = []
 bad = 0
 for case in range(n_cases):
-    h = int(rng.integers(48, 420)); w = int(rng.integers(48, 520))
+    h = int(rng.integers(48, max_h)); w = int(rng.integers(48, max_w))
     if case % 3 == 0: w = (w // 4) * 4                      # the tile kernel needs w % 4 == 0; other widths take the generic path
     p = dict(B.FB_PARAMS)
     kind = case % 5
