@@ -11,6 +11,7 @@ OPTFLOW_FARNEBACK_GAUSSIAN = 256
 BF_E_INVALID, BF_E_UNSUPPORTED, BF_E_NODEVICE = -1, -2, -3
 BF_DTYPE_U8, BF_DTYPE_F32 = 0, 1
 BF_PLAN_EXACT_F32 = 1
+BF_PROF_TAGS = ("iter_update", "iter_last", "update", "coarse", "expand")   # BF_PROF_* in include/btcsflow.h
 
 
 class BfParams(C.Structure):
@@ -52,6 +53,7 @@ _SIGNATURES = {
     "bf_plan_scale_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_d), C.POINTER(_i)]),
     "bf_plan_profile": (_i, [_vp, _i]),
     "bf_plan_profile_read": (_i, [_vp, C.POINTER(_i), C.POINTER(_d), C.POINTER(C.c_longlong)]),
+    "bf_plan_profile_tag": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "bf_launch_count": (C.c_longlong, []),
     "bf_launch_count_reset": (None, []),
     "bf_flow_pair": (_i, [_vp, _vp, _vp, _i, _sz, _vp, _vp]),

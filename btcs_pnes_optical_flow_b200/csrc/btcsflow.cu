@@ -15,11 +15,59 @@
 
 #include "farneback_kernels.cuh"
 #include "farneback_fast.cuh"
-#include "farneback_march.cuh"
 #include "pc1_kernels.cuh"
 #include "bandpass_kernels.cuh"
 
 namespace {
+
+// Grow-only device scratch for the stream-ordered entry points that are not tied to a plan (PC1, band-pass), one block per
+// (device, stream) and calling thread: calls on different streams never share a block, calls on one stream are ordered by
+// the stream itself.  (cudaMallocAsync/cudaFreeAsync would hand the memory back to the OS at every synchronisation --
+// default pool release threshold 0 -- and cost milliseconds per call on a KB-sized problem.)
+struct StreamScratch {
+    struct Block { int dev; cudaStream_t st; void* buf; size_t cap; };
+    std::vector<Block> blocks;
+    ~StreamScratch() { /* freed with the context at process exit; a thread's blocks cannot be freed safely while queued work may use them */ }
+    cudaError_t get(int dev, cudaStream_t st, size_t need, void** out) {
+        for (auto& b : blocks) {
+            if (b.dev != dev || b.st != st) continue;
+            if (b.cap < need) {
+                cudaError_t e = cudaStreamSynchronize(st);            // earlier work on this stream may still use the block
+                if (e != cudaSuccess) return e;
+                cudaFree(b.buf);
+                b.buf = nullptr; b.cap = 0;
+                e = cudaMalloc(&b.buf, need + need / 2);
+                if (e != cudaSuccess) return e;
+                b.cap = need + need / 2;
+            }
+            *out = b.buf;
+            return cudaSuccess;
+        }
+        if (blocks.size() >= 16) {                                    // bounded: recycle the oldest block
+            cudaError_t e = cudaStreamSynchronize(blocks.front().st);
+            if (e != cudaSuccess) cudaGetLastError();                 // the stream may have been destroyed: nothing left to wait for
+            cudaFree(blocks.front().buf);
+            blocks.erase(blocks.begin());
+        }
+        Block b{dev, st, nullptr, need + need / 2};
+        cudaError_t e = cudaMalloc(&b.buf, b.cap);
+        if (e != cudaSuccess) return e;
+        blocks.push_back(b);
+        *out = b.buf;
+        return cudaSuccess;
+    }
+};
+
+// device that owns a device pointer (the stream-ordered entry points run on the data's device, whatever is current)
+int device_of(const void* dptr, int* dev) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, dptr) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return cudaGetDevice(dev) == cudaSuccess ? 0 : 1;
+    }
+    *dev = at.device;
+    return 0;
+}
 
 thread_local std::string g_err;
 thread_local long long g_launches = 0;
@@ -185,9 +233,9 @@ struct ScaleInfo {
     float* tmpk = nullptr;                    // horizontal-pass scratch of this level [F][H][pitch] (levels coarser than 0)
     void* R = nullptr;                        // fp32 planes [F][5][h][pitch], or packed fp16 pixels [F][h][pitch] x 16 B
     float2* flow = nullptr;                   // [B][h][pitch]
-    // tensor maps for the tile kernel's L2 prefetch (compact plans): one per matrices buffer
+    // tensor maps for the tile kernel's L2 prefetch (compact plans, box window): one per matrices buffer
     bf::TileMaps maps[2];
-    int maps_th = 0;                          // tile height they were encoded for; 0 = none
+    bool have_maps = false;
 };
 
 template <typename T>
@@ -216,9 +264,17 @@ struct bf_plan {
     float* stage_flow = nullptr;
     uint8_t* pair_in[2] = {nullptr, nullptr};   // bf_flow_pair_host staging (H x W x 4 bytes each)
     float* pair_flow = nullptr;
-    double* d_ex = nullptr; double* d_ey = nullptr; int axes_cap = 0;
-    uint8_t* d_masks = nullptr; size_t masks_cap = 0;
-    float* d_out = nullptr; size_t out_cap = 0;
+    // per-call resources of the host series path, two slots used alternately (a call may be queued while the previous one
+    // still runs): device axes / masks / result, and a pinned host block the caller's (pageable) axes and masks are copied
+    // into so that their upload never blocks the host behind the stream's earlier work
+    struct HostSlot {
+        double* d_ex = nullptr; double* d_ey = nullptr; int axes_cap = 0;
+        uint8_t* d_masks = nullptr; size_t masks_cap = 0;
+        float* d_out = nullptr; size_t out_cap = 0;
+        uint8_t* pinned = nullptr; size_t pinned_cap = 0;
+        long long last_ticket = -1;                 // the call that used this slot last
+    } slot[2];
+    cudaEvent_t ev_aux = nullptr;                   // axes + masks of the current call have reached the device
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool ev_free_rec[2] = {false, false};       // staging buffer b has a pending "expansion done" event (also across calls)
@@ -228,11 +284,14 @@ struct bf_plan {
     bool use_fast = true;
     bool r_half = false;        // polynomial coefficients packed in 16 B per pixel, b f32 + A f16 (fast path, uint8 input)
     int sm_count = 148;
-    // dominant-kernel timing (bf_plan_profile)
+    // stage timing (bf_plan_profile): CUDA event pairs on the launch stream, tagged BF_PROF_*
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
+    std::vector<int> prof_tag, prof_np; // per pair of events
     size_t prof_used = 0;               // events in use
-    long long prof_pairs = 0;
+    int prof_n[BF_PROF_NTAGS] = {};     // results of the last bf_plan_profile_read
+    double prof_ms[BF_PROF_NTAGS] = {};
+    long long prof_pairs[BF_PROF_NTAGS] = {};
 };
 
 namespace {
@@ -298,56 +357,50 @@ int launch_polyexp(const float* I, int pitch, size_t frame_stride, int w, int h,
     return 0;
 }
 
-int launch_update(const bf::UpdateArgs& a, int np, bool r_half, cudaStream_t st) {
+// BTCSFLOW_PAIR_GROUP=g: pairs per group in the CTA order of the batched kernels (farneback_common.cuh, decode_cta)
+int pair_group() {
+    const char* e = getenv("BTCSFLOW_PAIR_GROUP");
+    const int v = e ? atoi(e) : 1;
+    return v >= 1 && v <= 64 ? v : 1;
+}
+
+int launch_update(const bf::UpdateArgs& a0, int np, bool r_half, cudaStream_t st) {
+    bf::UpdateArgs a = a0;
+    a.np = np; a.pair_group = pair_group();
     dim3 b(64, 4);
-    dim3 g(cdiv(a.w, 64), cdiv(a.h, 4 * bf::kUpdRows), np);
+    const unsigned g = (unsigned)(cdiv(a.w, 64) * cdiv(a.h, 4 * bf::kUpdRows)) * (unsigned)np;
     if (r_half) bf::k_update<true><<<g, b, 0, st>>>(a);
     else bf::k_update<false><<<g, b, 0, st>>>(a);
     LAUNCH_CHECK();
     return 0;
 }
 
-// Which kernel runs one blur+solve(+update) iteration: the tile kernel (default), the warp-specialised strip-marching
-// kernel (BTCSFLOW_KERNEL=march), or the runtime-parameter kernel (BTCSFLOW_NO_FAST=1 / unsupported parameters).
-enum BlurKernel { BK_GENERIC = 0, BK_TILE = 1, BK_MARCH = 2, BK_GAUSS = 3 };
-
-int sm_count_cached() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
+// Which kernel runs one blur+solve(+update) iteration: a compile-time-window tile kernel (box or Gaussian, half windows
+// 2..16) or the runtime-parameter kernel (BTCSFLOW_NO_FAST=1, other windows, unaligned stage-API buffers).
+enum BlurKernel { BK_GENERIC = 0, BK_TILE = 1, BK_GAUSS = 3 };
 
 BlurKernel choose_blur_kernel(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, bool allow_fast) {
-    if (!allow_fast) return BK_GENERIC;
-    const char* e = getenv("BTCSFLOW_KERNEL");                      // read per call: tests flip it within a process
-    const int pref = (e && strcmp(e, "march") == 0) ? BK_MARCH : BK_TILE;   // tile kernel measured faster (profiles/)
-    if (bf::gauss_fast_supported(wc)) return BK_GAUSS;              // winsize 20/21 Gaussian window (config C4)
-    if (pref == BK_MARCH && bf::march_supported(wc, a)) return BK_MARCH;
-    if (bf::blur_solve_fast_supported(wc, a.pitch) && bf::blur_solve_fast_aligned(a)) return BK_TILE;
+    if (!allow_fast || !bf::tile_fast_aligned(a)) return BK_GENERIC;
+    if (bf::gauss_fast_supported(wc)) return BK_GAUSS;
+    if (bf::box_fast_supported(wc, a.pitch)) return BK_TILE;
     return BK_GENERIC;
 }
 
-int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast, bool r_half) {
+int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, bool allow_fast, bool r_half) {
     switch (choose_blur_kernel(a, wc, allow_fast)) {
-        case BK_MARCH: return bf::march_ncta(a.w, a.h, np, sm_count_cached());
-        case BK_TILE: return bf::blur_solve_fast_ncta(a.w, a.h, r_half);
+        case BK_TILE: return bf::box_fast_ncta(a.w, a.h, r_half);
         case BK_GAUSS: return bf::gauss_fast_ncta(a.w, a.h);
         default: return cdiv(a.w, bf::kBsTW) * cdiv(a.h, bf::kBsTH);
     }
 }
 
-int launch_blur_solve(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, int np, bool allow_fast, bool r_half,
-                      cudaStream_t st, const bf::TileMaps* maps = nullptr, int maps_th = 0) {
+int launch_blur_solve(const bf::BlurSolveArgs& a0, const bf::WinCoef& wc, int np, bool allow_fast, bool r_half,
+                      cudaStream_t st, const bf::TileMaps* maps = nullptr) {
+    bf::BlurSolveArgs a = a0;
+    a.np = np; a.pair_group = pair_group();
     switch (choose_blur_kernel(a, wc, allow_fast)) {
-        case BK_MARCH:
-            bf::launch_march(a, wc, np, sm_count_cached(), r_half, st);
-            break;
         case BK_TILE:
-            bf::launch_blur_solve_fast(a, wc, np, r_half, st, maps, maps_th);
+            bf::launch_box_fast(a, wc, np, r_half, st, maps);
             break;
         case BK_GAUSS:
             bf::launch_gauss_fast(a, wc, np, r_half, st);
@@ -430,6 +483,29 @@ int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_
     return 0;
 }
 
+int prof_begin(bf_plan* p, int tag, int np, cudaStream_t st) {
+    if (!p->prof_on) return 0;
+    if (p->prof_used + 2 > p->prof_ev.size()) {
+        for (int e = 0; e < 2; ++e) {
+            cudaEvent_t ev;
+            CU(cudaEventCreate(&ev));
+            p->prof_ev.push_back(ev);
+        }
+        p->prof_tag.push_back(0);
+        p->prof_np.push_back(0);
+    }
+    p->prof_tag[p->prof_used / 2] = tag;
+    p->prof_np[p->prof_used / 2] = np;
+    CU(cudaEventRecord(p->prof_ev[p->prof_used], st));
+    return 0;
+}
+int prof_end(bf_plan* p, cudaStream_t st) {
+    if (!p->prof_on) return 0;
+    CU(cudaEventRecord(p->prof_ev[p->prof_used + 1], st));
+    p->prof_used += 2;
+    return 0;
+}
+
 struct RoiCtx {
     const uint8_t* masks = nullptr;  // [n_roi][H][W]
     int n_roi = 0;
@@ -474,7 +550,7 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
     for (int i = 0; i < nsc; ++i) {
         const ScaleInfo& s = p->sc[i];
         const bool finest = (i == nsc - 1);
-        const size_t m_stride = 5 * s.plane;
+        const size_t m_stride = p->r_half ? bf::m_pair_bytes<true>(s.plane) : bf::m_pair_bytes<false>(s.plane);
         bf::UpdateArgs u{};
         u.R = s.R; u.plane_stride = s.plane; u.slot_stride = p->r_half ? s.plane : 5 * s.plane; u.slot0 = slot0; u.nslots = p->F;
         u.pitch = s.pitch; u.w = s.w; u.h = s.h;
@@ -488,8 +564,11 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
             u.tab = bf::ResizeTab{s.fix, s.fax, s.fiy, s.fay};
         }
         u.M = p->M[0]; u.m_stride = m_stride;
-        int rc = launch_update(u, np, p->r_half, st);
+        int rc = prof_begin(p, finest ? BF_PROF_UPDATE : BF_PROF_COARSE, np, st);
         if (rc) return rc;
+        rc = launch_update(u, np, p->r_half, st);
+        if (rc) return rc;
+        if ((rc = prof_end(p, st))) return rc;
         for (int it = 0; it < I; ++it) {
             const bool last = (it == I - 1);
             bf::BlurSolveArgs a{};
@@ -508,26 +587,12 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
                     a.axes = p->axes; a.partial = p->partial;
                 }
             }
-            const bool prof = p->prof_on && finest;
-            if (prof) {
-                if (p->prof_used + 2 > p->prof_ev.size()) {
-                    for (int e = 0; e < 2; ++e) {
-                        cudaEvent_t ev;
-                        CU(cudaEventCreate(&ev));
-                        p->prof_ev.push_back(ev);
-                    }
-                }
-                CU(cudaEventRecord(p->prof_ev[p->prof_used], st));
-            }
-            rc = launch_blur_solve(a, p->wc, np, p->use_fast, p->r_half, st, s.maps_th ? &s.maps[it & 1] : nullptr, s.maps_th);
+            if ((rc = prof_begin(p, finest ? (last ? BF_PROF_ITER_LAST : BF_PROF_ITER_UPDATE) : BF_PROF_COARSE, np, st))) return rc;
+            rc = launch_blur_solve(a, p->wc, np, p->use_fast, p->r_half, st, s.have_maps ? &s.maps[it & 1] : nullptr);
             if (rc) return rc;
-            if (prof) {
-                CU(cudaEventRecord(p->prof_ev[p->prof_used + 1], st));
-                p->prof_used += 2;
-                p->prof_pairs += np;
-            }
+            if ((rc = prof_end(p, st))) return rc;
             if (last && finest && want_roi) {
-                const int ncta = blur_solve_ncta(a, p->wc, np, p->use_fast, p->r_half);
+                const int ncta = blur_solve_ncta(a, p->wc, p->use_fast, p->r_half);
                 bf::k_roi_finalize<<<cdiv(np * roi->n_roi, 4), 128, 0, st>>>(p->partial, np, roi->n_roi, ncta, roi->ex,
                                                                              roi->ey, t0 + 1, roi->out, roi->T);
                 LAUNCH_CHECK();
@@ -657,35 +722,32 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
         cudaMemset(s.flow, 0, (size_t)p->B * s.plane * sizeof(float2));
     }
     const ScaleInfo& fine = p->sc.back();
-    size_t tmp_elems = 0, m_elems = 0;
+    size_t tmp_elems = 0, m_bytes = 0;
     for (auto& s : p->sc) {
         tmp_elems = std::max(tmp_elems, (size_t)p->F * height * s.pitch);
-        m_elems = std::max(m_elems, (size_t)p->B * 5 * s.plane);
+        m_bytes = std::max(m_bytes, (size_t)p->B * (p->r_half ? bf::m_pair_bytes<true>(s.plane) : bf::m_pair_bytes<false>(s.plane)));
     }
     if ((rc = plan_alloc(p, &p->tmp, tmp_elems))) return cleanup_fail(rc);
     for (int i = 0; i < 2; ++i) {
         uint8_t* mbuf = nullptr;
-        const size_t mbytes = m_elems * (p->r_half ? sizeof(__half) : sizeof(float));
-        if ((rc = plan_alloc(p, &mbuf, mbytes))) return cleanup_fail(rc);
-        cudaMemset(mbuf, 0, mbytes);
+        if ((rc = plan_alloc(p, &mbuf, m_bytes))) return cleanup_fail(rc);
+        cudaMemset(mbuf, 0, m_bytes);
         p->M[i] = mbuf;
     }
     // Tensor maps for the tile kernel's L2 prefetch (compact plans; BTCSFLOW_TMAP=0 keeps the per-row requests).
     {
         const char* e = getenv("BTCSFLOW_TMAP");
-        if (p->r_half && p->use_fast && !(e && e[0] == '0')) {
-            const int th = bf::tile_th(true);
+        if (p->r_half && p->use_fast && bf::box_fast_supported(p->wc, 32) && !(e && e[0] == '0')) {
+            const int th = bf::box_tile_th(true);
             for (auto& s : p->sc) {
-                if (!bf::blur_solve_fast_shape(s.w, s.h)) continue;
-                if (bf::encode_tile_maps(&s.maps[0], p->M[0], s.R, s.w, s.h, s.pitch, s.plane, p->B, p->F, th) &&
-                    bf::encode_tile_maps(&s.maps[1], p->M[1], s.R, s.w, s.h, s.pitch, s.plane, p->B, p->F, th))
-                    s.maps_th = th;
+                if (!bf::tile_fast_shape(s.w, s.h)) continue;
+                s.have_maps = bf::encode_tile_maps(&s.maps[0], p->M[0], s.R, s.w, s.h, s.pitch, s.plane, p->B, p->F, p->wc.m, th) &&
+                              bf::encode_tile_maps(&s.maps[1], p->M[1], s.R, s.w, s.h, s.pitch, s.plane, p->B, p->F, p->wc.m, th);
             }
         }
     }
     if ((rc = plan_alloc(p, &p->axes, (size_t)p->B * 4))) return cleanup_fail(rc);
-    p->ncta_max = std::max({cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), cdiv(fine.w, bf::kFbTW) * cdiv(fine.h, 16),
-                            cdiv(fine.w, bf::kFbTW) * 16});
+    p->ncta_max = std::max(cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), cdiv(fine.w, bf::kFbTW) * cdiv(fine.h, 16));
     if ((rc = plan_alloc(p, &p->partial, (size_t)p->B * std::max(max_rois, 1) * p->ncta_max * bf::kRoiVals))) return cleanup_fail(rc);
     if (cudaDeviceSynchronize() != cudaSuccess) return cleanup_fail(fail(2, "plan initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out = p;
@@ -703,7 +765,11 @@ int bf_plan_destroy(bf_plan* p) {
     cudaFree(p->tmp); cudaFree(p->M[0]); cudaFree(p->M[1]); cudaFree(p->axes); cudaFree(p->partial);
     cudaFree(p->stage[0]); cudaFree(p->stage[1]); cudaFree(p->stage_flow);
     cudaFree(p->pair_in[0]); cudaFree(p->pair_in[1]); cudaFree(p->pair_flow);
-    cudaFree(p->d_ex); cudaFree(p->d_ey); cudaFree(p->d_masks); cudaFree(p->d_out);
+    for (auto& hs : p->slot) {
+        cudaFree(hs.d_ex); cudaFree(hs.d_ey); cudaFree(hs.d_masks); cudaFree(hs.d_out);
+        if (hs.pinned) cudaFreeHost(hs.pinned);
+    }
+    if (p->ev_aux) cudaEventDestroy(p->ev_aux);
     for (int i = 0; i < 2; ++i) {
         if (p->ev_copied[i]) cudaEventDestroy(p->ev_copied[i]);
         if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]);
@@ -726,18 +792,29 @@ int bf_plan_profile_read(bf_plan* p, int* n_launches, double* total_ms, long lon
     int rc = check_plan(p);
     if (rc) return rc;
     DeviceGuard dg(p->device);
-    double tot = 0;
+    for (int t = 0; t < BF_PROF_NTAGS; ++t) { p->prof_n[t] = 0; p->prof_ms[t] = 0; p->prof_pairs[t] = 0; }
     for (size_t i = 0; i + 1 < p->prof_used; i += 2) {
         CU(cudaEventSynchronize(p->prof_ev[i + 1]));
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, p->prof_ev[i], p->prof_ev[i + 1]));
-        tot += ms;
+        const int t = p->prof_tag[i / 2];
+        p->prof_n[t] += 1;
+        p->prof_ms[t] += ms;
+        p->prof_pairs[t] += p->prof_np[i / 2];
     }
-    if (n_launches) *n_launches = (int)(p->prof_used / 2);
-    if (total_ms) *total_ms = tot;
-    if (pair_iterations) *pair_iterations = p->prof_pairs;
+    if (n_launches) *n_launches = p->prof_n[BF_PROF_ITER_UPDATE] + p->prof_n[BF_PROF_ITER_LAST];
+    if (total_ms) *total_ms = p->prof_ms[BF_PROF_ITER_UPDATE] + p->prof_ms[BF_PROF_ITER_LAST];
+    if (pair_iterations) *pair_iterations = p->prof_pairs[BF_PROF_ITER_UPDATE] + p->prof_pairs[BF_PROF_ITER_LAST];
     p->prof_used = 0;
-    p->prof_pairs = 0;
+    return 0;
+}
+
+int bf_plan_profile_tag(const bf_plan* p, int tag, int* n_launches, double* total_ms, long long* pairs) {
+    if (!p) return fail(BF_E_INVALID, "plan is NULL");
+    if (tag < 0 || tag >= BF_PROF_NTAGS) return fail(BF_E_INVALID, "unknown profile tag %d", tag);
+    if (n_launches) *n_launches = p->prof_n[tag];
+    if (total_ms) *total_ms = p->prof_ms[tag];
+    if (pairs) *pairs = p->prof_pairs[tag];
     return 0;
 }
 
@@ -827,8 +904,10 @@ int bf_flow_series(bf_plan* p, const uint8_t* frames, int T, const double* ex, c
         const int np = std::min(p->B, T - 1 - t0);
         const int tf = (t0 == 0) ? 0 : t0 + 1;  // frame t0 of a later batch is already expanded (ring)
         const int nf = t0 + np - tf + 1;
+        if ((rc = prof_begin(p, BF_PROF_EXPAND, nf, st))) return rc;
         rc = expand_frames<uint8_t>(p, frames + (size_t)tf * fb, (size_t)p->W, fb, tf, nf, st);
         if (rc) return rc;
+        if ((rc = prof_end(p, st))) return rc;
         rc = run_pairs(p, t0, np, flow_out ? flow_out + (size_t)t0 * fb * 2 : nullptr, n_roi > 0 ? &roi : nullptr, st);
         if (rc) return rc;
     }
@@ -886,35 +965,54 @@ int bf_flow_series_host_async(bf_plan* p, const uint8_t* frames, int T, const do
         CU(cudaEventRecord(p->ev_copied[b], p->copy_stream));
         return 0;
     };
-    // The first chunk's frames are queued on the copy stream BEFORE the ROI masks and axes go up: those come from pageable
-    // memory (staged, synchronous copies, ~0.3 ms for a 1080p mask) and would otherwise delay the first frame.
+    // Calls on one plan share its workspace: whatever stream this call is given, it starts after the previous call's work.
+    if (p->next_ticket > 0) CU(cudaStreamWaitEvent(st, p->ev_done[(p->next_ticket - 1) % bf_plan::kTickets], 0));
+    // The first chunk's frames are queued on the copy stream BEFORE the ROI masks and axes: the first frame should not wait.
     if (T > 1 && (rc = issue_copy(0, 0))) return rc;
+    bool aux_pending = false;
     if (n_roi > 0) {
-        if (p->axes_cap < T) {
-            cudaFree(p->d_ex); cudaFree(p->d_ey); p->d_ex = p->d_ey = nullptr;
-            CU(cudaMalloc((void**)&p->d_ex, (size_t)T * 2 * sizeof(double)));
-            CU(cudaMalloc((void**)&p->d_ey, (size_t)T * 2 * sizeof(double)));
-            p->axes_cap = T;
+        bf_plan::HostSlot& hs = p->slot[p->next_ticket & 1];
+        // the slot's buffers may still be read by the call that used it last (two calls back): wait for that one only
+        if (hs.last_ticket >= 0) CU(cudaEventSynchronize(p->ev_done[hs.last_ticket % bf_plan::kTickets]));
+        if (hs.axes_cap < T) {
+            cudaFree(hs.d_ex); cudaFree(hs.d_ey); hs.d_ex = hs.d_ey = nullptr;
+            CU(cudaMalloc((void**)&hs.d_ex, (size_t)T * 2 * sizeof(double)));
+            CU(cudaMalloc((void**)&hs.d_ey, (size_t)T * 2 * sizeof(double)));
+            hs.axes_cap = T;
         }
         const size_t mb = (size_t)n_roi * fb;
-        if (p->masks_cap < mb) {
-            cudaFree(p->d_masks); p->d_masks = nullptr;
-            CU(cudaMalloc((void**)&p->d_masks, mb));
-            p->masks_cap = mb;
+        if (hs.masks_cap < mb) {
+            cudaFree(hs.d_masks); hs.d_masks = nullptr;
+            CU(cudaMalloc(&hs.d_masks, mb));
+            hs.masks_cap = mb;
         }
         const size_t ob = (size_t)n_roi * T * 3;
-        if (p->out_cap < ob) {
-            cudaFree(p->d_out); p->d_out = nullptr;
-            CU(cudaMalloc((void**)&p->d_out, ob * sizeof(float)));
-            p->out_cap = ob;
+        if (hs.out_cap < ob) {
+            cudaFree(hs.d_out); hs.d_out = nullptr;
+            CU(cudaMalloc((void**)&hs.d_out, ob * sizeof(float)));
+            hs.out_cap = ob;
         }
-        CU(cudaMemcpyAsync(p->d_ex, ex, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(p->d_ey, ey, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(p->d_masks, roi_masks, mb, cudaMemcpyHostToDevice, st));
+        const size_t ab = (size_t)T * 2 * sizeof(double);
+        if (hs.pinned_cap < 2 * ab + mb) {
+            if (hs.pinned) cudaFreeHost(hs.pinned);
+            hs.pinned = nullptr;
+            CU(cudaMallocHost((void**)&hs.pinned, 2 * ab + mb));
+            hs.pinned_cap = 2 * ab + mb;
+        }
+        memcpy(hs.pinned, ex, ab);
+        memcpy(hs.pinned + ab, ey, ab);
+        memcpy(hs.pinned + 2 * ab, roi_masks, mb);
+        CU(cudaMemcpyAsync(hs.d_ex, hs.pinned, ab, cudaMemcpyHostToDevice, p->copy_stream));
+        CU(cudaMemcpyAsync(hs.d_ey, hs.pinned + ab, ab, cudaMemcpyHostToDevice, p->copy_stream));
+        CU(cudaMemcpyAsync(hs.d_masks, hs.pinned + 2 * ab, mb, cudaMemcpyHostToDevice, p->copy_stream));
+        if (!p->ev_aux) CU(cudaEventCreateWithFlags(&p->ev_aux, cudaEventDisableTiming));
+        CU(cudaEventRecord(p->ev_aux, p->copy_stream));
+        aux_pending = true;
         const int n = (int)ob;
-        bf::k_fill_nan<<<cdiv(n, 256), 256, 0, st>>>(p->d_out, n);
+        bf::k_fill_nan<<<cdiv(n, 256), 256, 0, st>>>(hs.d_out, n);
         LAUNCH_CHECK();
-        roi.masks = p->d_masks; roi.n_roi = n_roi; roi.ex = p->d_ex; roi.ey = p->d_ey; roi.out = p->d_out; roi.T = T;
+        hs.last_ticket = p->next_ticket;
+        roi.masks = hs.d_masks; roi.n_roi = n_roi; roi.ex = hs.d_ex; roi.ey = hs.d_ey; roi.out = hs.d_out; roi.T = T;
     }
     int chunk = 0;
     for (int t0 = 0; t0 < T - 1; ++chunk) {
@@ -925,10 +1023,13 @@ int bf_flow_series_host_async(bf_plan* p, const uint8_t* frames, int T, const do
         // the NEXT chunk's copy is queued before this chunk's ~45 launches so that the copy stream stays a chunk ahead
         if (t0 + np < T - 1 && (rc = issue_copy(chunk + 1, t0 + np))) return rc;
         CU(cudaStreamWaitEvent(st, p->ev_copied[b], 0));
+        if ((rc = prof_begin(p, BF_PROF_EXPAND, nf, st))) return rc;
         rc = expand_frames<uint8_t>(p, p->stage[b], (size_t)p->W, fb, tf, nf, st);
         if (rc) return rc;
+        if ((rc = prof_end(p, st))) return rc;
         CU(cudaEventRecord(p->ev_free[b], st));
         p->ev_free_rec[b] = true;
+        if (aux_pending) { CU(cudaStreamWaitEvent(st, p->ev_aux, 0)); aux_pending = false; }
         rc = run_pairs(p, t0, np, flow_out ? p->stage_flow : nullptr, n_roi > 0 ? &roi : nullptr, st);
         if (rc) return rc;
         if (flow_out)
@@ -937,7 +1038,7 @@ int bf_flow_series_host_async(bf_plan* p, const uint8_t* frames, int T, const do
         t0 += np;
     }
     if (n_roi > 0)
-        CU(cudaMemcpyAsync(out, p->d_out, (size_t)n_roi * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out, roi.out, (size_t)n_roi * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     const int slot = (int)(p->next_ticket % bf_plan::kTickets);
     if (!p->ev_done[slot]) CU(cudaEventCreateWithFlags(&p->ev_done[slot], cudaEventDisableTiming));
     CU(cudaEventRecord(p->ev_done[slot], st));
@@ -976,50 +1077,47 @@ int bf_pc1_sliding_batched(const double* vx, const double* vy, int n_series, int
     if (min_samples < 1) return fail(BF_E_INVALID, "min_samples must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return 0;
-    std::vector<bf::Pc1Cfg> cfgs(n_cfg);
-    int Ktot = 0, Kmax = 0;
-    for (int c = 0; c < n_cfg; ++c) {
+    for (int c = 0; c < n_cfg; ++c)
         if (win_n[c] < 1 || step_n[c] < 1) return fail(BF_E_INVALID, "win_n and step_n must be >= 1");
-        // optical_PCA.py:171-172,181: fewer than MIN_SAMPLES samples, or n < win_n -> no windows -> all NaN
-        int K = 0;
-        if (n >= min_samples && n >= win_n[c]) K = (n - win_n[c]) / step_n[c] + 1;
-        cfgs[c] = bf::Pc1Cfg{win_n[c], step_n[c], K, Ktot};
-        Ktot += K;
-        Kmax = std::max(Kmax, K);
-    }
-    const size_t nw = (size_t)n_series * std::max(Ktot, 1);
-    // Grow-only per-thread scratch: cudaMallocAsync/cudaFreeAsync would hand the memory back to the OS at every
-    // synchronisation (default pool release threshold 0) and cost milliseconds per call on a KB-sized problem.
-    struct Scratch { void* buf = nullptr; size_t cap = 0; int dev = -1; };
-    static thread_local Scratch sc;
+    static thread_local StreamScratch scratch;
     int dev = 0;
-    CU(cudaGetDevice(&dev));
-    const size_t cfg_bytes = round_up(n_cfg * (int)sizeof(bf::Pc1Cfg), 256);
-    const size_t need = cfg_bytes + 4 * nw * sizeof(double) + (2 * nw + (size_t)n_series * n_cfg) * sizeof(int);
-    if (sc.dev != dev || sc.cap < need) {
-        if (sc.buf) { CU(cudaDeviceSynchronize()); cudaFree(sc.buf); sc.buf = nullptr; sc.cap = 0; }
-        CU(cudaMalloc(&sc.buf, need + need / 2));
-        sc.cap = need + need / 2;
-        sc.dev = dev;
-    }
-    bf::Pc1Cfg* d_cfg = reinterpret_cast<bf::Pc1Cfg*>(sc.buf);
-    double* d_w = reinterpret_cast<double*>(static_cast<char*>(sc.buf) + cfg_bytes);   // wx, wy, cwx, cwy
-    int* d_i = reinterpret_cast<int*>(d_w + 4 * nw);                                   // valid, cen, nvalid
-    // pageable source: staged before the call returns, so the vector may die afterwards
-    CU(cudaMemcpyAsync(d_cfg, cfgs.data(), n_cfg * sizeof(bf::Pc1Cfg), cudaMemcpyHostToDevice, st));
-    double *wx = d_w, *wy = d_w + nw, *cwx = d_w + 2 * nw, *cwy = d_w + 3 * nw;
-    int *valid = d_i, *cen = d_i + nw, *nvalid = d_i + 2 * nw;
-    if (Kmax > 0) {
-        dim3 gA(cdiv(Kmax, 128), n_series, n_cfg);
-        bf::k_pc1_windows<<<gA, 128, 0, st>>>(vx, vy, n_series, n, d_cfg, n_cfg, Ktot, ref_x, ref_y, min_samples, wx, wy, valid);
+    if (device_of(vx, &dev)) return fail(BF_E_NODEVICE, "no current CUDA device");
+    DeviceGuard dg(dev);
+    if (!dg.ok) return fail(BF_E_NODEVICE, "cudaSetDevice(%d) failed", dev);
+    // window configurations travel as kernel parameters, kPc1MaxCfg per round of launches
+    for (int c0 = 0; c0 < n_cfg; c0 += bf::kPc1MaxCfg) {
+        const int nc = std::min(bf::kPc1MaxCfg, n_cfg - c0);
+        bf::Pc1CfgPack pack{};
+        int Ktot = 0, Kmax = 0;
+        for (int c = 0; c < nc; ++c) {
+            // optical_PCA.py:171-172,181: fewer than MIN_SAMPLES samples, or n < win_n -> no windows -> all NaN
+            int K = 0;
+            if (n >= min_samples && n >= win_n[c0 + c]) K = (n - win_n[c0 + c]) / step_n[c0 + c] + 1;
+            pack.c[c] = bf::Pc1Cfg{win_n[c0 + c], step_n[c0 + c], K, Ktot};
+            Ktot += K;
+            Kmax = std::max(Kmax, K);
+        }
+        const size_t nw = (size_t)n_series * std::max(Ktot, 1);
+        const size_t need = 4 * nw * sizeof(double) + (2 * nw + (size_t)n_series * nc) * sizeof(int);
+        void* buf = nullptr;
+        CU(scratch.get(dev, st, need, &buf));
+        double* d_w = static_cast<double*>(buf);                                           // wx, wy, cwx, cwy
+        int* d_i = reinterpret_cast<int*>(d_w + 4 * nw);                                   // valid, cen, nvalid
+        double *wx = d_w, *wy = d_w + nw, *cwx = d_w + 2 * nw, *cwy = d_w + 3 * nw;
+        int *valid = d_i, *cen = d_i + nw, *nvalid = d_i + 2 * nw;
+        if (Kmax > 0) {
+            dim3 gA(cdiv(Kmax, 128), n_series, nc);
+            bf::k_pc1_windows<<<gA, 128, 0, st>>>(vx, vy, n_series, n, pack, nc, Ktot, ref_x, ref_y, min_samples, wx, wy, valid);
+            LAUNCH_CHECK();
+        }
+        dim3 gB(n_series, nc);
+        bf::k_pc1_chain<<<gB, 1024, 1024 * sizeof(int), st>>>(pack, nc, Ktot, wx, wy, valid, cwx, cwy, cen, nvalid);
+        LAUNCH_CHECK();
+        dim3 gC(cdiv(n, 256), n_series, nc);
+        bf::k_pc1_project<<<gC, 256, 0, st>>>(vx, vy, n_series, n, pack, nc, Ktot, cwx, cwy, cen, nvalid,
+                                               pc1_out + (size_t)c0 * n_series * n);
         LAUNCH_CHECK();
     }
-    dim3 gB(n_series, n_cfg);
-    bf::k_pc1_chain<<<gB, 1024, 1024 * sizeof(int), st>>>(d_cfg, n_cfg, Ktot, wx, wy, valid, cwx, cwy, cen, nvalid);
-    LAUNCH_CHECK();
-    dim3 gC(cdiv(n, 256), n_series, n_cfg);
-    bf::k_pc1_project<<<gC, 256, 0, st>>>(vx, vy, n_series, n, d_cfg, n_cfg, Ktot, cwx, cwy, cen, nvalid, pc1_out);
-    LAUNCH_CHECK();
     return 0;
 }
 
@@ -1111,18 +1209,15 @@ int bf_bandpass_nanrobust(const double* x, int n_series, int n, const double* so
     }
     // same length rules as the reference: sos_required_padlen = 3 * (2 * n_sections) (optical_PCA.py:74-80, 107, 114)
     const int max_pad = 3 * (2 * n_sections), min_len = max_pad + 1;
-    struct Scratch { double* buf = nullptr; size_t cap = 0; int dev = -1; };
-    static thread_local Scratch sc;
+    static thread_local StreamScratch scratch;
     int dev = 0;
-    CU(cudaGetDevice(&dev));
+    if (device_of(x, &dev)) return fail(BF_E_NODEVICE, "no current CUDA device");
+    DeviceGuard dg(dev);
+    if (!dg.ok) return fail(BF_E_NODEVICE, "cudaSetDevice(%d) failed", dev);
     const int stride = n + 2 * max_pad + 8;
     const size_t need = (size_t)n_series * stride;
-    if (sc.dev != dev || sc.cap < need) {
-        if (sc.buf) { CU(cudaDeviceSynchronize()); cudaFree(sc.buf); sc.buf = nullptr; sc.cap = 0; }
-        CU(cudaMalloc((void**)&sc.buf, (need + need / 2) * sizeof(double)));
-        sc.cap = need + need / 2;
-        sc.dev = dev;
-    }
+    struct { double* buf; } sc{nullptr};
+    CU(scratch.get(dev, st, need * sizeof(double), (void**)&sc.buf));
     bf::k_bandpass_nanrobust<<<n_series, 32, 0, st>>>(x, n, c, min_len, max_pad, y, sc.buf, stride);
     LAUNCH_CHECK();
     return 0;

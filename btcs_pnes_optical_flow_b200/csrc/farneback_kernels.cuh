@@ -1,52 +1,9 @@
 // Farneback dense optical flow: generic (runtime-parameter) CUDA kernels for sm_100a.
-//
-// Algorithm restated from the validated behavioural spec of cv2.calcOpticalFlowFarneback (the single
-// hot call of the reference, /root/reference/optical_flow.py:173; spec in SURVEY.md Appendix A).
-// Data layout in HBM:
-//   level image  I   [frame][h][pitch] f32
-//   poly coeffs  R   exact plans:   [slot][5][h][pitch] f32 planes (b_y, b_x, A_yy, A_xx, A_xy)
-//                    compact plans: [slot][h][pitch] x 16 B per pixel (RPix: b in fp32, A in fp16), one LDG.128 per bilinear tap
-//   matrices     M   [pair][5][h][pitch] planes (G11, G12, G22, h1, h2): f32 (exact) or fp16 (compact)
-//   flow             [pair][h][pitch] float2 (dx, dy)
-// `pitch` is in elements and a multiple of 32 for plan-owned buffers.  Kernels templated on RH = compact storage.
+// Layouts and the shared device code: farneback_common.cuh.
 #pragma once
-#include <cuda_fp16.h>
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include <type_traits>
+#include "farneback_common.cuh"
 
 namespace bf {
-
-constexpr int kMaxPolyN = 16;
-constexpr int kMaxWinHalf = 64;
-
-struct PolyCoef {
-    float g[kMaxPolyN + 1];
-    float xg[kMaxPolyN + 1];
-    float xxg[kMaxPolyN + 1];
-    float ig11, ig03, ig33, ig55;
-    int n;
-};
-
-struct WinCoef {
-    float ker[kMaxWinHalf + 1];  // Gaussian window taps ker[0..m] (normalised); unused for box
-    float scale;                 // box: 1 / winsize^2 ; Gaussian: 1
-    int m;                       // half window
-    int gauss;
-};
-
-__device__ __forceinline__ int reflect101(int i, int n) {
-    if (n == 1) return 0;
-    while (i < 0 || i >= n) {
-        if (i < 0) i = -i;
-        if (i >= n) i = 2 * (n - 1) - i;
-    }
-    return i;
-}
-
-__device__ __forceinline__ float load_px(const uint8_t* p) { return (float)(*p); }
-__device__ __forceinline__ float load_px(const float* p) { return *p; }
 
 // ---------------------------------------------------------------------------------------------------
 // K1a: horizontal part of (GaussianBlur REFLECT_101 -> bilinear resize), evaluated only at the columns
@@ -194,241 +151,6 @@ __global__ void __launch_bounds__(256) k_polyexp_generic(const float* __restrict
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// UpdateMatrices for one pixel: bilinear gather of R1 at (x+dx, y+dy), fallback branch when
-// the 2x2 footprint is not strictly inside, border attenuation in the outer 5 px.
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float border_w(int i, int n) {
-    // table {0.14, 0.14, 0.4472, 0.4472, 0.4472}
-    float s = 1.f;
-    if (i < 5) s *= (i < 2) ? 0.14f : 0.4472f;
-    const int j = n - 1 - i;
-    if (j < 5) s *= (j < 2) ? 0.14f : 0.4472f;
-    return s;
-}
-
-// Addressing: `plane` and `pitch` are 32-bit element counts and every pointer is formed as base + c*plane + offset
-// with an unsigned 32-bit offset, which ptxas turns into one IMAD.WIDE per pair of loads (a 64-bit size_t
-// formulation costs ~55 integer instructions per pixel here; measured with ncu, see profiles/).
-__device__ __forceinline__ void update_px(const float* __restrict__ R0, const float* __restrict__ R1,
-                                          unsigned plane, unsigned pitch, int w, int h, int x, int y,
-                                          float dx, float dy, float out[5]) {
-    float q[5];
-    {
-        const float* pq = R0 + ((unsigned)y * pitch + (unsigned)x);
-#pragma unroll
-        for (int c = 0; c < 5; ++c) { q[c] = __ldg(pq); pq += plane; }
-    }
-    float fx = (float)x + dx, fy = (float)y + dy;
-    const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
-    fx -= (float)x1;
-    fy -= (float)y1;
-    float r2, r3, r4, r5, r6;
-    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-        const float* pa = R1 + ((unsigned)y1 * pitch + (unsigned)x1);
-        float t0[5], t1[5], b0[5], b1[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const float* pb = pa + pitch;
-            t0[c] = __ldg(pa); t1[c] = __ldg(pa + 1);
-            b0[c] = __ldg(pb); b1[c] = __ldg(pb + 1);
-            pa += plane;
-        }
-        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        float rw[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) rw[c] = a00 * t0[c] + a01 * t1[c] + a10 * b0[c] + a11 * b1[c];
-        r2 = rw[0];
-        r3 = rw[1];
-        r4 = (q[2] + rw[2]) * 0.5f;
-        r5 = (q[3] + rw[3]) * 0.5f;
-        r6 = (q[4] + rw[4]) * 0.25f;
-    } else {
-        r2 = r3 = 0.f;
-        r4 = q[2];
-        r5 = q[3];
-        r6 = q[4] * 0.5f;
-    }
-    r2 = (q[0] - r2) * 0.5f;
-    r3 = (q[1] - r3) * 0.5f;
-    r2 += r4 * dy + r6 * dx;
-    r3 += r6 * dy + r5 * dx;
-    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-        const float sc = border_w(x, w) * border_w(y, h);
-        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
-    }
-    out[0] = r4 * r4 + r6 * r6;
-    out[1] = (r4 + r5) * r6;
-    out[2] = r5 * r5 + r6 * r6;
-    out[3] = r4 * r2 + r6 * r3;
-    out[4] = r6 * r2 + r5 * r3;
-}
-
-// Compact plans (RH) also keep the matrices M as fp16 planes: |M| <= ~1.3e3 for uint8 frames (max over the probe set,
-// DESIGN.md), far from fp16 overflow; values below fp16's subnormal range vanish against the 1e-3 regulariser.  Measured
-// cost with both R and M in fp16: <= 3e-4 px mean, 2.2e-3 px max at 10 px flows (gate: 0.01 / 0.05).  Sums stay fp32.
-template <bool RH> struct MStore { using type = typename std::conditional<RH, __half, float>::type; };
-
-__device__ __forceinline__ float m_to_float(float v) { return v; }
-__device__ __forceinline__ float m_to_float(__half v) { return __half2float(v); }
-__device__ __forceinline__ void m_from_float(float* p, float v) { *p = v; }
-__device__ __forceinline__ void m_from_float(__half* p, float v) { *p = __float2half_rn(v); }
-__device__ __forceinline__ float4 m_load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 m_load4(const __half* p) {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
-    union { unsigned v; __half2 h; } a, b;
-    a.v = u.x; b.v = u.y;
-    const float2 lo = __half22float2(a.h), hi = __half22float2(b.h);
-    return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-
-template <typename MT>
-__device__ __forceinline__ void store_m(MT* __restrict__ M, unsigned plane, unsigned o, const float m[5]) {
-    MT* pm = M + o;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) { m_from_float(pm, m[c]); pm += plane; }
-}
-
-// ---- packed polynomial coefficients: 16 bytes per pixel, one 128-bit load per bilinear tap ------------------------
-// Storage format only: all arithmetic stays fp32.  The linear terms b (whose frame-to-frame DIFFERENCE drives the flow)
-// stay fp32; the quadratic terms A, which only enter through averages, are fp16: (b_y f32, b_x f32, (A_yy, A_xx) f16x2,
-// (A_xy, 0) f16x2).  Against the earlier all-fp16 pixel this unpacks with 3 conversions per tap instead of 5 and removes
-// most of the storage error (tests/test_gpu_flow.py).  It turns the 20 scalar gather loads + 5 centre
-// loads per pixel of the planar layout into 4 + 1 LDG.128.  Used for uint8 input only (|A| is bounded by the 0..255 range).
-struct __align__(16) RPix { float by, bx; __half2 ayy_axx, axy_0; };
-
-__device__ __forceinline__ uint4 pack_r(float r0, float r1, float r2, float r3, float r4) {
-    union { unsigned v; __half2 h; } a, b;
-    a.h = __floats2half2_rn(r2, r3);
-    b.h = __floats2half2_rn(r4, 0.f);
-    return make_uint4(__float_as_uint(r0), __float_as_uint(r1), a.v, b.v);
-}
-
-__device__ __forceinline__ void unpack_r(const uint4& u, float v[5]) {
-    union { unsigned v; __half2 h; } a, b;
-    a.v = u.z; b.v = u.w;
-    const float2 q = __half22float2(a.h);
-    v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = q.x; v[3] = q.y; v[4] = __low2float(b.h);
-}
-
-// UpdateMatrices for one pixel from packed R (same arithmetic as update_px).  R0/R1 point at pixel (0,0) of the frame.
-template <bool BORDER = true>
-__device__ __forceinline__ void update_px_h(const uint4* __restrict__ R0, const uint4* __restrict__ R1, unsigned pitch,
-                                            int w, int h, int x, int y, float dx, float dy, float out[5]) {
-    float q[5];
-    unpack_r(__ldg(R0 + (unsigned)y * pitch + (unsigned)x), q);
-    float fx = (float)x + dx, fy = (float)y + dy;
-    const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
-    fx -= (float)x1;
-    fy -= (float)y1;
-    float r2, r3, r4, r5, r6;
-    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-        const uint4* pa = R1 + (unsigned)y1 * pitch + (unsigned)x1;
-        const uint4 u00 = __ldg(pa), u01 = __ldg(pa + 1), u10 = __ldg(pa + pitch), u11 = __ldg(pa + pitch + 1);
-        float t00[5], t01[5], t10[5], t11[5];
-        unpack_r(u00, t00); unpack_r(u01, t01); unpack_r(u10, t10); unpack_r(u11, t11);
-        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        float rw[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) rw[c] = a00 * t00[c] + a01 * t01[c] + a10 * t10[c] + a11 * t11[c];
-        r2 = rw[0];
-        r3 = rw[1];
-        r4 = (q[2] + rw[2]) * 0.5f;
-        r5 = (q[3] + rw[3]) * 0.5f;
-        r6 = (q[4] + rw[4]) * 0.25f;
-    } else {
-        r2 = r3 = 0.f;
-        r4 = q[2];
-        r5 = q[3];
-        r6 = q[4] * 0.5f;
-    }
-    r2 = (q[0] - r2) * 0.5f;
-    r3 = (q[1] - r3) * 0.5f;
-    r2 += r4 * dy + r6 * dx;
-    r3 += r6 * dy + r5 * dx;
-    if (BORDER && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
-        const float sc = border_w(x, w) * border_w(y, h);
-        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
-    }
-    out[0] = r4 * r4 + r6 * r6;
-    out[1] = (r4 + r5) * r6;
-    out[2] = r5 * r5 + r6 * r6;
-    out[3] = r4 * r2 + r6 * r3;
-    out[4] = r6 * r2 + r5 * r3;
-}
-
-// The same update split in two so that the gather of the NEXT pixel is in flight while this one is being computed (the
-// one-piece version issues its four taps inside the `inside` branch, so every pixel pays a full L2 round trip in series;
-// ncu source page, profiles/).  Branch-free: the taps are always fetched from a clamped footprint (requires w, h >= 2)
-// and the fallback branch becomes five selects.  Arithmetic and operation order are those of update_px_h.
-struct UpdTaps { uint4 q, u00, u01, u10, u11; float fx, fy, dx, dy; bool inside; };
-
-__device__ __forceinline__ void update_issue_h(const uint4* __restrict__ R0, const uint4* __restrict__ R1, unsigned pitch,
-                                               int w, int h, int x, int y, float dx, float dy, UpdTaps& t) {
-    t.q = __ldg(R0 + (unsigned)y * pitch + (unsigned)x);
-    const float fx = (float)x + dx, fy = (float)y + dy;
-    const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
-    t.fx = fx - (float)x1;
-    t.fy = fy - (float)y1;
-    t.dx = dx; t.dy = dy;
-    t.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-    const int cx = min(max(x1, 0), w - 2), cy = min(max(y1, 0), h - 2);
-    const uint4* pa = R1 + (unsigned)cy * pitch + (unsigned)cx;
-    t.u00 = __ldg(pa); t.u01 = __ldg(pa + 1); t.u10 = __ldg(pa + pitch); t.u11 = __ldg(pa + pitch + 1);
-}
-
-template <bool BORDER>
-__device__ __forceinline__ void update_finish_h(const UpdTaps& t, int w, int h, int x, int y, float out[5]) {
-    float q[5], t00[5], t01[5], t10[5], t11[5];
-    unpack_r(t.q, q);
-    unpack_r(t.u00, t00); unpack_r(t.u01, t01); unpack_r(t.u10, t10); unpack_r(t.u11, t11);
-    const float fx = t.fx, fy = t.fy;
-    const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-    float rw[5];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) rw[c] = a00 * t00[c] + a01 * t01[c] + a10 * t10[c] + a11 * t11[c];
-    const bool in = t.inside;
-    float r2 = in ? rw[0] : 0.f;
-    float r3 = in ? rw[1] : 0.f;
-    float r4 = in ? (q[2] + rw[2]) * 0.5f : q[2];
-    float r5 = in ? (q[3] + rw[3]) * 0.5f : q[3];
-    float r6 = in ? (q[4] + rw[4]) * 0.25f : q[4] * 0.5f;
-    r2 = (q[0] - r2) * 0.5f;
-    r3 = (q[1] - r3) * 0.5f;
-    r2 += r4 * t.dy + r6 * t.dx;
-    r3 += r6 * t.dy + r5 * t.dx;
-    if (BORDER && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
-        const float sc = border_w(x, w) * border_w(y, h);
-        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
-    }
-    out[0] = r4 * r4 + r6 * r6;
-    out[1] = (r4 + r5) * r6;
-    out[2] = r5 * r5 + r6 * r6;
-    out[3] = r4 * r2 + r6 * r3;
-    out[4] = r6 * r2 + r5 * r3;
-}
-
-// R0/R1 of pair p in the frame ring (p < nslots, slot0 < nslots: one conditional subtract instead of an integer modulo).
-__device__ __forceinline__ int ring_slot(int slot0, int p, int nslots) {
-    const int s = slot0 + p;
-    return s >= nslots ? s - nslots : s;
-}
-
-// Layout-agnostic front end: RH = packed fp16 (slot_stride counts uint4 pixels), else fp32 planes (slot_stride in floats).
-// BORDER = false: the caller guarantees the pixel lies outside the 5-px attenuation ring (interior tiles).
-template <bool RH, bool BORDER = true>
-__device__ __forceinline__ void update_px_any(const void* R0, const void* R1, unsigned plane, unsigned pitch, int w, int h,
-                                              int x, int y, float dx, float dy, float out[5]) {
-    if (RH) update_px_h<BORDER>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), pitch, w, h, x, y, dx, dy, out);
-    else update_px(static_cast<const float*>(R0), static_cast<const float*>(R1), plane, pitch, w, h, x, y, dx, dy, out);
-}
-
-template <bool RH>
-__device__ __forceinline__ const void* r_slot_ptr(const void* R, size_t slot_stride, int slot) {
-    if (RH) return static_cast<const uint4*>(R) + (size_t)slot * slot_stride;
-    return static_cast<const float*>(R) + (size_t)slot * slot_stride;
-}
-
 struct ResizeTab {
     const int* ix; const float* ax;  // [w]
     const int* iy; const float* ay;  // [h]
@@ -436,12 +158,13 @@ struct ResizeTab {
 
 // K3a: M = UpdateMatrices(R0, R1, flow_init).  flow_mode: 0 = zero, 1 = flow buffer, 2 = upsample coarse.
 struct UpdateArgs {
+    int np, pair_group;                                                    // batch size and CTA order (decode_cta)
     const void* R; size_t plane_stride, slot_stride; int slot0, nslots;   // R0 = ring slot (slot0+p), R1 = the next one
     int pitch, w, h;
     int flow_mode;
     const float2* flow; int flow_pitch; size_t flow_stride;              // mode 1: [pair][h][flow_pitch]; mode 2: coarse
     int ws, hs; float mult; ResizeTab tab;
-    void* M; size_t m_stride;                                              // [pair][5][h][pitch] f32, or fp16 when RH
+    void* M; size_t m_stride;                                              // matrices, m_stride = BYTES per pair (MView)
     float2* flow_out; int flow_out_pitch; size_t flow_out_stride;          // optional: write flow_init
 };
 
@@ -452,20 +175,21 @@ constexpr int kUpdRows = 4;   // 8 rows: 74 registers, slower (18.1 vs 17.3 ms p
 
 template <bool RH>
 __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int yb = (blockIdx.y * blockDim.y + threadIdx.y) * kUpdRows;
-    const int p = blockIdx.z;
+    // block = 64 columns x (4 x kUpdRows) rows; 1-D grid in decode_cta order
+    const TilePos tp = decode_cta(blockIdx.x, (a.w + 63) / 64, (a.h + 4 * kUpdRows - 1) / (4 * kUpdRows), a.np, a.pair_group);
+    const int x = tp.bx * 64 + threadIdx.x;
+    const int yb = (tp.by * 4 + threadIdx.y) * kUpdRows;
+    const int p = tp.p;
     if (x >= a.w || yb >= a.h) return;
-    using MT = typename MStore<RH>::type;
     const int w = a.w, h = a.h;
     const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
     const void* R0 = nullptr;
     const void* R1 = nullptr;
-    MT* Mo = nullptr;
-    if (a.M) {
+    const bool want_m = a.M != nullptr;
+    const MView<RH> Mo(a.M, a.m_stride, p, plane);
+    if (want_m) {
         R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
         R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
-        Mo = static_cast<MT*>(a.M) + (size_t)p * a.m_stride;
     }
     const float2* fin = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
     float2* fout = a.flow_out ? a.flow_out + (size_t)p * a.flow_out_stride : nullptr;
@@ -511,8 +235,8 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         for (int k = 0; k < kUpdRows; ++k)
             if (yb + k < h) fout[(unsigned)(yb + k) * (unsigned)a.flow_out_pitch + (unsigned)x] = fl[k];
     }
-    if (!Mo) return;
-    if (RH && w >= 2 && h >= 2) {
+    if (!want_m) return;
+    if constexpr (RH) {
         // packed coefficients: row k+1's taps are in flight while row k is computed (update_issue_h / update_finish_h)
         const uint4* R0h = static_cast<const uint4*>(R0);
         const uint4* R1h = static_cast<const uint4*>(R1);
@@ -521,23 +245,23 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
 #pragma unroll
         for (int k = 0; k < kUpdRows; k += 2) {
             update_issue_h(R0h, R1h, pitch, w, h, x, min(yb + k + 1, h - 1), fl[k + 1].x, fl[k + 1].y, B);
-            float m[5];
+            MOut<true> m;
             if (inner) update_finish_h<false>(A, w, h, x, yb + k, m); else update_finish_h<true>(A, w, h, x, yb + k, m);
-            if (yb + k < h) store_m(Mo, plane, (unsigned)(yb + k) * pitch + (unsigned)x, m);
+            if (yb + k < h) m_store(Mo, (unsigned)(yb + k) * pitch + (unsigned)x, m);
             if (k + 2 < kUpdRows) update_issue_h(R0h, R1h, pitch, w, h, x, min(yb + k + 2, h - 1), fl[k + 2].x, fl[k + 2].y, A);
             if (inner) update_finish_h<false>(B, w, h, x, yb + k + 1, m); else update_finish_h<true>(B, w, h, x, yb + k + 1, m);
-            if (yb + k + 1 < h) store_m(Mo, plane, (unsigned)(yb + k + 1) * pitch + (unsigned)x, m);
+            if (yb + k + 1 < h) m_store(Mo, (unsigned)(yb + k + 1) * pitch + (unsigned)x, m);
         }
-        return;
-    }
+    } else {
 #pragma unroll
-    for (int k = 0; k < kUpdRows; ++k) {
-        const int y = yb + k;
-        if (y >= h) break;
-        float m[5];
-        if (inner) update_px_any<RH, false>(R0, R1, plane, pitch, w, h, x, y, fl[k].x, fl[k].y, m);
-        else update_px_any<RH, true>(R0, R1, plane, pitch, w, h, x, y, fl[k].x, fl[k].y, m);
-        store_m(Mo, plane, (unsigned)y * pitch + (unsigned)x, m);
+        for (int k = 0; k < kUpdRows; ++k) {
+            const int y = yb + k;
+            if (y >= h) break;
+            MOut<false> m;
+            if (inner) update_px_any<false, false>(R0, R1, plane, pitch, w, h, x, y, fl[k].x, fl[k].y, m);
+            else update_px_any<false, true>(R0, R1, plane, pitch, w, h, x, y, fl[k].x, fl[k].y, m);
+            m_store(Mo, (unsigned)y * pitch + (unsigned)x, m);
+        }
     }
 }
 
@@ -547,89 +271,20 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
 // (channel, column), exact first window then short-history sliding: no long-range cancellation).
 // Phase 2: horizontal sums from shared, accurate 2x2 solve.  Phase 3: fused tail.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kBsTW = 32, kBsTH = 8;
-constexpr int kRoiVals = 4;  // sum vx, sum vy, sum mag, count
-
-struct BlurSolveArgs {
-    const void* M; size_t m_stride, plane_stride; int pitch, w, h;         // f32 planes, or fp16 planes when RH
-    // outputs (each optional)
-    float2* flow; int flow_pitch; size_t flow_stride;
-    void* Mout;
-    const void* R; size_t slot_stride; int slot0, nslots;   // for Mout (fp32 planes, or packed fp16 pixels)
-    // ROI reduction (optional): masks [n_roi][h][w] u8; axes per pair; partial [pair][roi][ncta][4]
-    const uint8_t* masks; int n_roi; size_t mask_stride; int mask_pitch;
-    const float* axes;  // [pair][4] = ex0, ex1, ey0, ey1
-    float* partial;
-};
-
-// accurate a*b - c*d (Kahan): the structure-tensor determinant cancels heavily where the window holds
-// 1-D structure; cv2 does this solve in double.
-__device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
-    const float cd = c * d;
-    const float err = fmaf(-c, d, cd);
-    const float dop = fmaf(a, b, -cd);
-    return dop + err;
-}
-
-__device__ __forceinline__ float2 solve2x2(float g11, float g12, float g22, float h1, float h2) {
-    const float det = diff_of_products(g11, g22, g12, g12) + 1e-3f;
-    const float idet = 1.f / det;
-    float2 r;
-    r.x = diff_of_products(g11, h2, g12, h1) * idet;
-    r.y = diff_of_products(g22, h1, g12, h2) * idet;
-    return r;
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// block-wide ROI partial sums for one pixel per thread; writes partial[...][4] per CTA (deterministic).
-__device__ __forceinline__ void roi_reduce_store(const BlurSolveArgs& a, int p, int x, int y, bool valid,
-                                                 float2 fl, float* s_red /*[8][4]*/) {
-    const float* ax = a.axes + p * 4;
-    const float vx = fl.x * ax[0] + fl.y * ax[1];
-    const float vy = fl.x * ax[2] + fl.y * ax[3];
-    const float mg = sqrtf(vx * vx + vy * vy);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarp = blockDim.x >> 5;
-    const int ncta = gridDim.x * gridDim.y;
-    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-    for (int r = 0; r < a.n_roi; ++r) {
-        const bool in = valid && a.masks[(size_t)r * a.mask_stride + (size_t)y * a.mask_pitch + x] != 0;
-        const float s0 = warp_sum(in ? vx : 0.f), s1 = warp_sum(in ? vy : 0.f), s2 = warp_sum(in ? mg : 0.f),
-                    s3 = warp_sum(in ? 1.f : 0.f);
-        __syncthreads();
-        if (lane == 0) {
-            s_red[warp * 4 + 0] = s0; s_red[warp * 4 + 1] = s1; s_red[warp * 4 + 2] = s2; s_red[warp * 4 + 3] = s3;
-        }
-        __syncthreads();
-        if (threadIdx.x < 4) {
-            float t = 0.f;
-            for (int i = 0; i < nwarp; ++i) t += s_red[i * 4 + threadIdx.x];
-            a.partial[(((size_t)p * a.n_roi + r) * ncta + cta) * kRoiVals + threadIdx.x] = t;
-        }
-    }
-}
-
 template <bool RH>
 __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs a, const WinCoef wc) {
     __shared__ float V[5][kBsTH][kBsTW + 2 * kMaxWinHalf];
-    __shared__ float s_red[8 * 4];
+    __shared__ float s_red[8 * 8];
     const int m = wc.m;
     const int x0 = blockIdx.x * kBsTW, y0 = blockIdx.y * kBsTH;
     const int p = blockIdx.z;
-    using MT = typename MStore<RH>::type;
-    const MT* Mp = static_cast<const MT*>(a.M) + (size_t)p * a.m_stride;
+    const MView<RH> Mp(const_cast<void*>(a.M), a.m_stride, p, (unsigned)a.plane_stride);
     const int tw = kBsTW + 2 * m;
     const int w = a.w, h = a.h;
     for (int it = threadIdx.x; it < 5 * tw; it += blockDim.x) {
         const int c = it / tw, tx = it - c * tw;
         const int gx = min(max(x0 - m + tx, 0), w - 1);
-        const MT* col = Mp + c * a.plane_stride + gx;
-        auto at = [&](int row) { return m_to_float(col[(size_t)row * a.pitch]); };
+        auto at = [&](int row) { return Mp.load(c, (unsigned)row * (unsigned)a.pitch + (unsigned)gx); };
         if (wc.gauss) {
             for (int ty = 0; ty < kBsTH; ++ty) {
                 const int gy = min(y0 + ty, h - 1);
@@ -673,10 +328,9 @@ __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs 
         if (a.Mout) {
             const void* R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
             const void* R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
-            float mm[5];
-            update_px_any<RH>(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, w, h, x, y, fl.x, fl.y, mm);
-            store_m(static_cast<MT*>(a.Mout) + (size_t)p * a.m_stride, (unsigned)a.plane_stride,
-                    (unsigned)y * (unsigned)a.pitch + (unsigned)x, mm);
+            MOut<RH> mm;
+            update_px_any<RH, true>(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, w, h, x, y, fl.x, fl.y, mm);
+            m_store(MView<RH>(a.Mout, a.m_stride, p, (unsigned)a.plane_stride), (unsigned)y * (unsigned)a.pitch + (unsigned)x, mm);
         }
     }
     if (a.partial) roi_reduce_store(a, p, x, y, valid, fl, s_red);
@@ -684,7 +338,7 @@ __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs 
 
 // Projection + ROI partial sums of an existing flow buffer (iterations == 0 path; same partial layout).
 __global__ void __launch_bounds__(256) k_roi_from_flow(const BlurSolveArgs a) {
-    __shared__ float s_red[8 * 4];
+    __shared__ float s_red[8 * 8];
     const int tx = threadIdx.x & (kBsTW - 1), ty = threadIdx.x / kBsTW;
     const int x = blockIdx.x * kBsTW + tx, y = blockIdx.y * kBsTH + ty;
     const int p = blockIdx.z;
@@ -694,8 +348,9 @@ __global__ void __launch_bounds__(256) k_roi_from_flow(const BlurSolveArgs a) {
     roi_reduce_store(a, p, x, y, valid, fl, s_red);
 }
 
-// Finalise the ROI means: out[roi][t_first+p][3] = sums / count.  One warp per (pair, roi); lanes stride over the
-// per-CTA partials and accumulate in double, then a fixed-order shuffle tree: deterministic run to run.
+// Finalise the ROI means: out[roi][t_first+p][3] = sums / counts (np.nanmean of each array: NaN samples were skipped, a
+// ROI without samples gives NaN).  One warp per (pair, roi); lanes stride over the per-CTA partials and accumulate in
+// double, then a fixed-order shuffle tree: deterministic run to run.
 __global__ void k_roi_finalize(const float* __restrict__ partial, int n_pairs, int n_roi, int ncta,
                                const double* __restrict__ ex, const double* __restrict__ ey, int t_first,
                                float* __restrict__ out, int T) {
@@ -704,28 +359,23 @@ __global__ void k_roi_finalize(const float* __restrict__ partial, int n_pairs, i
     if (i >= n_pairs * n_roi) return;
     const int p = i / n_roi, r = i - p * n_roi;
     const float4* q = reinterpret_cast<const float4*>(partial + (size_t)i * ncta * kRoiVals);
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    double s[6] = {0, 0, 0, 0, 0, 0};
     for (int c = lane; c < ncta; c += 32) {
-        const float4 v = q[c];
-        s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+        const float4 u = q[2 * c], v = q[2 * c + 1];
+        s[0] += u.x; s[1] += u.y; s[2] += u.z; s[3] += u.w; s[4] += v.x; s[5] += v.y;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
     }
     if (lane != 0) return;
     const int t = t_first + p;
     float* o = out + ((size_t)r * T + t) * 3;
     const bool ok = isfinite(ex[2 * t]) && isfinite(ex[2 * t + 1]) && isfinite(ey[2 * t]) && isfinite(ey[2 * t + 1]);
-    if (!ok || s3 == 0.0) {
-        const float nanv = __int_as_float(0x7fc00000);
-        o[0] = o[1] = o[2] = nanv;
-    } else {
-        o[0] = (float)(s0 / s3); o[1] = (float)(s1 / s3); o[2] = (float)(s2 / s3);
-    }
+    const float nanv = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = (ok && s[3 + k] > 0.0) ? (float)(s[k] / s[3 + k]) : nanv;
 }
 
 // axes[p] = (float)ex[t], ... for pairs t = t_first + p (python float -> float32 as numpy does, optical_flow.py:180-181)

@@ -1,0 +1,769 @@
+// Tile kernels with a compile-time window: one fused Farneback iteration per launch.
+//
+// k_blur_solve_box<MH>: flow = Solve(BoxBlur_{2MH+1}(M)) fused with M' = UpdateMatrices(flow) and/or the
+// body-axis projection + ROI partial sums (reference call site optical_flow.py:173, reduction
+// optical_flow.py:176-187).  One CTA = 128 x TH output pixels (compact plans: TH = 16, 256 threads, 4 CTAs per SM).
+//   phase 0  tensor-map prefetches (UTMAPF) bring the M tile (G planes, h planes) and the R0 / R1 blocks into L2.
+//   phase 1  vertical window sums, global -> shared.  One thread per (channel, column group): the 2MH+1 row window lives
+//            in registers (fully unrolled ring), 8 bytes per row -- four fp16 columns of a G plane (consumed by FHADD, no
+//            conversions) or two fp32 columns of an h plane -- so the 3 x 36 + 2 x 72 = 252 tasks of a tile fill the 256
+//            threads; exact first window then add-new/subtract-old with a history bounded by the TH+2MH rows of the tile:
+//            no long-range cancellation, and all-zero (static) regions stay exactly zero.
+//   phase 2  horizontal window sums from shared with conflict-free LDS.128 (lane stride 16 B), 4 outputs per
+//            thread sharing the common partial sum (no subtraction), then the 2x2 solve with Kahan-accurate
+//            determinants.  The 1/winsize^2 scale is folded into the regulariser (reg = 1e-3 * winsize^4).
+//   phase 3  flow is transposed through shared memory so that lanes own consecutive pixels again: coalesced R0
+//            loads, bilinear R1 gather issued one pixel ahead, M' stores; ROI sums reduced per CTA (deterministic partials).
+#pragma once
+#include <cstdlib>
+#include <cstring>
+
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include "farneback_common.cuh"
+
+namespace bf {
+
+constexpr int kFbTW = 128, kFbTH = 32;
+
+template <int MH, int TH, bool RH>
+struct FastBoxCfg {
+    static constexpr int HALO = (MH + 3) / 4 * 4;
+    static constexpr int D = HALO - MH;                        // unused leading columns in the halo
+    static constexpr int NC4 = (kFbTW + 2 * HALO) / 4;         // 4-column groups per tile row
+    static constexpr int NC2 = 2 * NC4;                        // 2-column groups per tile row
+    static constexpr int VP = kFbTW + 2 * HALO + 4;            // shared row pitch (floats, multiple of 4)
+    static constexpr int WIN = 2 * MH + 1;
+    static constexpr int NCH = (D + 2 * MH + 3) / 4 + 1;       // float4 chunks a 4-output group reads
+    static constexpr int V_FLOATS = 5 * TH * VP;
+    static constexpr int NTASK = RH ? 3 * NC4 + 2 * NC2 : 5 * NC4;   // phase-1 column tasks per tile
+    static constexpr int PF = TH >= 32 ? 8 : 4;                // register prefetch depth in phase 1
+    // CTAs per SM: what registers (window = WIN rows x 2 registers compact, x 4 exact) and shared memory allow
+    static constexpr int WREG = WIN * (RH ? 2 : 4);
+    static constexpr int CTAS_REG = WREG <= 30 ? 4 : (WREG <= 46 ? 3 : (WREG <= 84 ? 2 : 1));
+    static constexpr size_t SMEM = (size_t)(V_FLOATS + 64) * sizeof(float);
+    static constexpr int CTAS_SMEM = (int)((227u * 1024u) / (SMEM + 1024u));
+    static constexpr int CTAS = CTAS_REG < CTAS_SMEM ? CTAS_REG : (CTAS_SMEM < 1 ? 1 : CTAS_SMEM);
+    static_assert(MH >= 2 && MH <= 16, "half window out of range for the fast path");
+    static_assert(TH % 8 == 0, "tile height must be a multiple of 8");
+    static_assert((size_t)TH * kFbTW * sizeof(float2) <= (size_t)V_FLOATS * sizeof(float), "F must fit in V");
+};
+
+// Debug builds (-DBF_TRACE, tools/trace_phases.py): thread 0 of every CTA of k_blur_solve_box stamps the SM clock at the
+// phase boundaries so that phase durations and the overlap of co-resident CTAs can be read off directly.
+#ifdef BF_TRACE
+__device__ unsigned long long* bf_trace_buf = nullptr;
+__device__ __forceinline__ void trace_stamp(int slot, bool on) {
+    if (threadIdx.x == 0 && on && bf_trace_buf) {
+        const size_t cta = blockIdx.x;
+        unsigned long long t;
+        if (slot == 0) {
+            unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            bf_trace_buf[cta * 8 + 6] = t;
+            bf_trace_buf[cta * 8 + 7] = sm;
+        }
+        bf_trace_buf[cta * 8 + slot] = clock64();
+    }
+}
+#define BF_TRACE_STAMP(k) trace_stamp(k, a.Mout != nullptr)   // launches with the update tail only
+#else
+#define BF_TRACE_STAMP(k)
+#endif
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// A whole 4-D box (tile of M with its halo: x, y, channel, pair; block of R: 4 words, x, y, ring slot) requested into L2
+// by ONE instruction through a tensor map; parts of the box outside the tensor are skipped by the hardware.  (Per-line
+// prefetch.global.L2 costs one L1 tag cycle per 128-byte line, ~2700 cycles of a CTA's 40 000-cycle life; per-row
+// cp.async.bulk.prefetch.L2 is worse -- a uniform-operand instruction wrapped in a lane loop; profiles/r1s.)
+__device__ __forceinline__ void prefetch_l2_box(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// Tensor maps of one launch of the tile kernels (built per scale at plan creation, bf::encode_tile_maps):
+// g / hh = input matrices, fp16 G planes {x, y, 3, pair} and fp32 h planes {x, y, 2, pair}, boxes (TW + 2 HALO) x
+// (TH + 2 MH) x channels x 1; r0 / r1 = packed R ring {128 words = 32 pixels, x / 32, y, slot}, boxes 128 x 4 x TH x 1
+// and 128 x 6 x (TH + 4) x 1.
+struct TileMaps { CUtensorMap g, hh, r0, r1; };
+
+// ---- one row of a column group as it sits in the phase-1 register window ----------------------------------------------
+// RowH4: four fp16 columns kept packed (uint2), consumed by the mixed-precision add of sm_100a (FHADD: f32 + f16 -> f32,
+// exact conversion included): no separate conversions and half the window registers.  RowF2 / RowF4: fp32 columns.
+struct RowH4 {
+    using Elem = __half; using Sum = float4;
+    static constexpr int GW = 4;
+    uint2 v;
+    static __device__ __forceinline__ RowH4 load(const __half* p) { return RowH4{__ldg(reinterpret_cast<const uint2*>(p))}; }
+    __device__ __forceinline__ void split(unsigned short h[4]) const { split_h2(v.x, h[0], h[1]); split_h2(v.y, h[2], h[3]); }
+    __device__ __forceinline__ float4 first() const {
+        unsigned short h[4]; split(h);
+        return make_float4(fh_add(h[0], 0.f), fh_add(h[1], 0.f), fh_add(h[2], 0.f), fh_add(h[3], 0.f));
+    }
+    __device__ __forceinline__ void add_to(float4& s) const {
+        unsigned short h[4]; split(h);
+        s.x = fh_add(h[0], s.x); s.y = fh_add(h[1], s.y); s.z = fh_add(h[2], s.z); s.w = fh_add(h[3], s.w);
+    }
+    static __device__ __forceinline__ void slide(float4& s, const RowH4& nv, const RowH4& ov) {     // nv - (ov - s)
+        unsigned short n[4], o[4]; nv.split(n); ov.split(o);
+        s.x = fh_sub(n[0], fh_sub(o[0], s.x)); s.y = fh_sub(n[1], fh_sub(o[1], s.y));
+        s.z = fh_sub(n[2], fh_sub(o[2], s.z)); s.w = fh_sub(n[3], fh_sub(o[3], s.w));
+    }
+};
+struct RowF2 {
+    using Elem = float; using Sum = float2;
+    static constexpr int GW = 2;
+    float2 v;
+    static __device__ __forceinline__ RowF2 load(const float* p) { return RowF2{__ldg(reinterpret_cast<const float2*>(p))}; }
+    __device__ __forceinline__ float2 first() const { return v; }
+    __device__ __forceinline__ void add_to(float2& s) const { s.x += v.x; s.y += v.y; }
+    static __device__ __forceinline__ void slide(float2& s, const RowF2& nv, const RowF2& ov) {
+        s.x += nv.v.x - ov.v.x; s.y += nv.v.y - ov.v.y;
+    }
+};
+struct RowF4 {
+    using Elem = float; using Sum = float4;
+    static constexpr int GW = 4;
+    float4 v;
+    static __device__ __forceinline__ RowF4 load(const float* p) { return RowF4{__ldg(reinterpret_cast<const float4*>(p))}; }
+    __device__ __forceinline__ float4 first() const { return v; }
+    __device__ __forceinline__ void add_to(float4& s) const { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    static __device__ __forceinline__ void slide(float4& s, const RowF4& nv, const RowF4& ov) {
+        s.x += nv.v.x - ov.v.x; s.y += nv.v.y - ov.v.y; s.z += nv.v.z - ov.v.z; s.w += nv.v.w - ov.v.w;
+    }
+};
+
+// Store the window sums of one column group.  EDGE: the group may lie outside the image (mode 1 = left of it: splat lane 0
+// of the first group; 2 = right of it: splat lane kl of the last group) or straddle the right edge (3: lanes above kl take
+// lane kl) -- replicate border; the splat commutes with the sum, so the load path stays branch-free.
+template <bool EDGE>
+__device__ __forceinline__ void sum_store(float* dst, const float4& s, int mode, int kl) {
+    if (!EDGE || mode == 0) {
+        *reinterpret_cast<float4*>(dst) = s;
+    } else {
+        const float e = (mode == 1 || kl == 0) ? s.x : (kl == 1 ? s.y : (kl == 2 ? s.z : s.w));
+        const bool keep = mode == 3;
+        *reinterpret_cast<float4*>(dst) = make_float4(keep ? s.x : e, (keep && kl >= 1) ? s.y : e, (keep && kl >= 2) ? s.z : e, e);
+    }
+}
+template <bool EDGE>
+__device__ __forceinline__ void sum_store(float* dst, const float2& s, int mode, int kl) {
+    if (!EDGE || mode == 0) {
+        *reinterpret_cast<float2*>(dst) = s;
+    } else {
+        const float e = (mode == 1 || kl == 0) ? s.x : s.y;
+        *reinterpret_cast<float2*>(dst) = make_float2(mode == 3 ? s.x : e, e);
+    }
+}
+
+// Vertical (2MH+1)-row box sums of one column group for TH consecutive output rows; register ring window, software
+// prefetch PF rows ahead.  ROWS_IN: the tile's rows (with halo) lie inside the image, `src` already points at the first
+// halo row.  Otherwise rows are clamped to [0, h-1] (replicate) starting from row `yb`.
+template <int MH, bool ROWS_IN, bool EDGE, int TH, int PF, typename Row>
+__device__ __forceinline__ void vertical_box_sums(const typename Row::Elem* __restrict__ src, unsigned pitch, int yb, int h,
+                                                  int mode, int kl, float* __restrict__ dst, int vp) {
+    constexpr int WIN = 2 * MH + 1, NROW = TH + 2 * MH;
+    auto ld = [&](int i) -> Row {
+        if (ROWS_IN) return Row::load(src + (unsigned)i * pitch);
+        const int r = min(max(yb + i, 0), h - 1);
+        return Row::load(src + (unsigned)r * pitch);
+    };
+    Row win[WIN];
+#pragma unroll
+    for (int i = 0; i < WIN; ++i) win[i] = ld(i);
+    typename Row::Sum s = win[0].first();
+#pragma unroll
+    for (int i = 1; i < WIN; ++i) win[i].add_to(s);
+    sum_store<EDGE>(dst, s, mode, kl);
+    Row pre[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) pre[i] = ld(min(WIN + i, NROW - 1));
+#pragma unroll
+    for (int j = 1; j < TH; ++j) {
+        const Row nv = pre[(j - 1) % PF];
+        if (j - 1 + PF + WIN < NROW) pre[(j - 1) % PF] = ld(WIN + j - 1 + PF);
+        const Row ov = win[(j - 1) % WIN];
+        Row::slide(s, nv, ov);
+        win[(j - 1) % WIN] = nv;
+        sum_store<EDGE>(dst + j * vp, s, mode, kl);
+    }
+}
+
+// One phase-1 task: the column group that starts at image column gx (aligned to the image origin, possibly outside).
+template <int MH, int TH, int PF, typename Row>
+__device__ __forceinline__ void column_task(const typename Row::Elem* __restrict__ plane_base, unsigned pitch, int w, int h, int gx,
+                                            int y0, bool rows_in, float* __restrict__ dst, int vp) {
+    constexpr int GW = Row::GW;
+    const int wl = (w - 1) & ~(GW - 1), kl = (w - 1) & (GW - 1);      // last group that holds a pixel, and that pixel's lane
+    const int mode = gx < 0 ? 1 : (gx > wl ? 2 : ((gx == wl && kl != GW - 1) ? 3 : 0));
+    const int cgx = mode == 1 ? 0 : (mode == 2 ? wl : gx);
+    const typename Row::Elem* src = plane_base + (unsigned)cgx;
+    // rows inside / clamped x interior column / replicated edge column (edge columns are rare and were costing 7.5 FSEL per
+    // pixel when handled by selects)
+    if (mode == 0 && rows_in) vertical_box_sums<MH, true, false, TH, PF, Row>(src + (unsigned)(y0 - MH) * pitch, pitch, 0, 0, 0, 0, dst, vp);
+    else vertical_box_sums<MH, false, true, TH, PF, Row>(src, pitch, y0 - MH, h, mode, kl, dst, vp);
+}
+
+// Lines of R that a block of rows [ya, ya+NROWS) x columns [x0, x0+128) will touch in its update tail: R0 under the
+// block, R1 within +-2 rows / +-32 columns (larger flows simply miss).  Requested into L2 ahead of use (launches without
+// tensor maps: stage API, fp32 R planes).
+template <bool RH, int NROWS>
+__device__ __forceinline__ void prefetch_r_block(const void* R0v, const void* R1v, unsigned plane, unsigned pitch, int w, int h,
+                                                 int x0, int ya, int tid, int nthreads) {
+    if (RH) {
+        const uint4* R0 = static_cast<const uint4*>(R0v);
+        const uint4* R1 = static_cast<const uint4*>(R1v);
+        const int xmax = max(w - 1, 0);                                  // 8 pixels per 128-byte line, 16 lines per row
+        for (int e = tid; e < NROWS * 16; e += nthreads) {
+            const int yy = min(ya + (e >> 4), h - 1), xx = min(x0 + (e & 15) * 8, xmax);
+            prefetch_l2(R0 + (unsigned)yy * pitch + (unsigned)xx);
+        }
+        for (int e = tid; e < (NROWS + 4) * 24; e += nthreads) {
+            const int r = e / 24, l = e - r * 24;
+            const int yy = min(max(ya - 2 + r, 0), h - 1), xx = min(max(x0 - 32 + l * 8, 0), xmax);
+            prefetch_l2(R1 + (unsigned)yy * pitch + (unsigned)xx);
+        }
+    } else {
+        const float* R0 = static_cast<const float*>(R0v);
+        const float* R1 = static_cast<const float*>(R1v);
+        const int xmax = max((int)pitch - 32, 0);
+        for (int e = tid; e < NROWS * 4; e += nthreads) {                // 4 lines per row and plane
+            const int yy = min(ya + (e >> 2), h - 1), xx = min(x0 + (e & 3) * 32, xmax);
+            const float* q = R0 + (unsigned)yy * pitch + (unsigned)xx;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) prefetch_l2(q + (size_t)c * plane);
+        }
+        for (int e = tid; e < (NROWS + 4) * 6; e += nthreads) {
+            const int r = e / 6, l = e - r * 6;
+            const int yy = min(max(ya - 2 + r, 0), h - 1), xx = min(max(x0 - 32 + l * 32, 0), xmax);
+            const float* q = R1 + (unsigned)yy * pitch + (unsigned)xx;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) prefetch_l2(q + (size_t)c * plane);
+        }
+    }
+}
+
+// M tile (with halo) into L2, per 128-byte line (launches without tensor maps).
+template <bool RH, int MH, int HALO, int TH>
+__device__ __forceinline__ void prefetch_m_tile(const MView<RH>& Mv, unsigned pitch, int w, int h, int x0, int y0, int tid, int nthreads) {
+    constexpr int NROW = TH + 2 * MH;
+    constexpr int NL = (kFbTW + 2 * HALO) / 32 + 2;                     // 128-byte lines of fp32 per tile row (incl. misalignment)
+    const int xlo = max(x0 - HALO, 0) & ~31, xmaxl = max((w - 1) & ~31, 0);
+    for (int e = tid; e < NROW * NL; e += nthreads) {
+        const int r = e / NL, l = e - r * NL;
+        const int yy = min(max(y0 - MH + r, 0), h - 1), xx = min(xlo + l * 32, xmaxl);
+        const unsigned o = (unsigned)yy * pitch + (unsigned)xx;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) prefetch_l2(Mv.hplane(c) + o);
+        if (!RH || (l & 1) == 0) {                                       // fp16 planes: a line holds 64 columns
+#pragma unroll
+            for (int c = 0; c < 3; ++c) prefetch_l2(Mv.gplane(c) + o);
+        }
+    }
+}
+
+// Update tail of one warp: N pixels per lane, lane = column within a 32-wide group, pixel i+1's taps in flight while
+// pixel i is computed.  EDGE: the tile may stick out of the image or touch the 5-px attenuation ring.
+template <bool EDGE, int N, typename RowFn, typename ColFn>
+__device__ __forceinline__ void update_tail_pipelined(const uint4* __restrict__ R0, const uint4* __restrict__ R1,
+                                                      const float2* __restrict__ F, const MView<true>& Mo,
+                                                      unsigned pitch, int w, int h, int x0, int y0, RowFn tail_row, ColFn tail_col) {
+    auto issue = [&](int i, UpdTaps& t) {
+        const int r = tail_row(i), cx = tail_col(i);
+        const float2 f = F[r * kFbTW + cx];
+        int x = x0 + cx, y = y0 + r;
+        if (EDGE) { x = min(x, w - 1); y = min(y, h - 1); }
+        update_issue_h(R0, R1, pitch, w, h, x, y, f.x, f.y, t);
+    };
+    auto finish = [&](int i, const UpdTaps& t) {
+        const int r = tail_row(i), cx = tail_col(i);
+        const int x = x0 + cx, y = y0 + r;
+        MOut<true> mm;
+        update_finish_h<EDGE>(t, w, h, x, y, mm);
+        if (!EDGE || (x < w && y < h)) m_store(Mo, (unsigned)y * pitch + (unsigned)x, mm);
+    };
+    UpdTaps A, B;
+    issue(0, A);
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        issue(i + 1, B);
+        finish(i, A);
+        if (i + 2 < N) issue(i + 2, A);
+        finish(i + 1, B);
+    }
+}
+
+// Phase 3 shared by the box and Gaussian tile kernels: flow F[TH][128] (shared) -> flow store / M' = UpdateMatrices /
+// projection + ROI partial sums.  A warp walks DOWN one 32-pixel column group (4 column groups x 2 row halves): the
+// bottom taps of row r are the top taps of row r + 1, so consecutive iterations of the same warp hit L1 instead of
+// fetching every R1 line twice from L2.
+template <bool RH, int TH>
+__device__ __forceinline__ void tile_tail(const BlurSolveArgs& a, const float2* __restrict__ F, float* __restrict__ s_red,
+                                          const void* R0, const void* R1, int x0, int y0, int p, int cta, int ncta) {
+    constexpr int N = TH / 2;                                  // pixels per thread: 8 warps = 4 column groups x 2 row halves
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int w = a.w, h = a.h;
+    const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
+    const int tail_r0 = (wid >> 2) * N, tail_c0 = (wid & 3) * 32 + lane;
+    auto tail_row = [&](int i) { return tail_r0 + i; };
+    auto tail_col = [&](int) { return tail_c0; };
+    if (a.flow || a.Mout) {
+        float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
+        const bool want_m = a.Mout != nullptr;
+        const MView<RH> Mo(a.Mout, a.m_stride, p, plane);
+        // interior tiles (85 % at 1080p): bounds and the 5-px attenuation ring are decided once per tile
+        const bool inner = (x0 >= 5) && (y0 >= 5) && (x0 + kFbTW <= w - 5) && (y0 + TH <= h - 5);
+        bool done = false;
+        if constexpr (RH) {
+            if (want_m && !fo) {
+                if (inner) update_tail_pipelined<false, N>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, pitch, w, h, x0, y0, tail_row, tail_col);
+                else update_tail_pipelined<true, N>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, pitch, w, h, x0, y0, tail_row, tail_col);
+                done = true;
+            }
+        }
+        if (!done) {
+#pragma unroll 4
+            for (int i = 0; i < N; ++i) {
+                const int r = tail_row(i), cx = tail_col(i);
+                const int x = x0 + cx, y = y0 + r;
+                if (x < w && y < h) {
+                    const float2 f = F[r * kFbTW + cx];
+                    if (fo) fo[(unsigned)y * (unsigned)a.flow_pitch + (unsigned)x] = f;
+                    if (want_m) {
+                        MOut<RH> mm;
+                        if (inner) update_px_any<RH, false>(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
+                        else update_px_any<RH, true>(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
+                        m_store(Mo, (unsigned)y * pitch + (unsigned)x, mm);
+                    }
+                }
+            }
+        }
+    }
+    if (a.partial) {
+        const float* ax = a.axes + p * 4;
+        const float e00 = ax[0], e01 = ax[1], e10 = ax[2], e11 = ax[3];
+        for (int roi = 0; roi < a.n_roi; ++roi) {
+            const uint8_t* mk = a.masks + (size_t)roi * a.mask_stride;
+            RoiAcc acc;
+#pragma unroll 4
+            for (int i = 0; i < N; ++i) {
+                const int r = tail_row(i), cx = tail_col(i);
+                const int x = x0 + cx, y = y0 + r;
+                if (x < w && y < h && mk[(size_t)y * a.mask_pitch + x] != 0) {
+                    const float2 f = F[r * kFbTW + cx];
+                    acc.add(f.x * e00 + f.y * e01, f.x * e10 + f.y * e11);
+                }
+            }
+            roi_cta_store(acc, s_red, a.partial + (((size_t)p * a.n_roi + roi) * ncta + cta) * kRoiVals);
+        }
+    }
+}
+
+// 2x2 solves of 4 adjacent outputs from their blurred matrices gs[channel][output]; flows to fl[4].
+template <bool RH>
+__device__ __forceinline__ void solve4(const float gs[5][4], float reg, float2 fl[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float g11 = gs[0][j], g12 = gs[1][j], g22 = gs[2][j], h1 = gs[3][j], h2 = gs[4][j];
+        const float det = diff_of_products(g11, g22, g12, g12) + reg;
+        // det >= reg > 0 and far from the denormal range: compact plans take the 1-ulp hardware reciprocal (the IEEE
+        // division costs ~9 instructions per pixel); exact plans keep the division
+        float idet;
+        if (RH) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(idet) : "f"(det));
+        else idet = 1.f / det;
+        fl[j].x = diff_of_products(g11, h2, g12, h1) * idet;
+        fl[j].y = diff_of_products(g22, h1, g12, h2) * idet;
+    }
+}
+
+template <int MH, bool RH, int TH>
+__global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg, const bool use_maps,
+                                                                                    const __grid_constant__ TileMaps maps) {
+    using C = FastBoxCfg<MH, TH, RH>;
+    constexpr int NT = 256, NW = 8, RG = TH / NW;
+    extern __shared__ __align__(16) float smem[];
+    float* V = smem;                                   // [5][TH][VP]
+    float2* F = reinterpret_cast<float2*>(smem);       // [TH][TW], aliases V after phase 2
+    float* s_red = smem + C::V_FLOATS;                 // [8][8]
+    const int tid = threadIdx.x;
+    const int w = a.w, h = a.h;
+    const int nbx = (w + kFbTW - 1) / kFbTW, nby = (h + TH - 1) / TH;
+    const TilePos tp = decode_cta(blockIdx.x, nbx, nby, a.np, a.pair_group);
+    const int x0 = tp.bx * kFbTW, y0 = tp.by * TH, p = tp.p;
+    const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
+    const MView<RH> Mv(const_cast<void*>(a.M), a.m_stride, p, plane);
+    BF_TRACE_STAMP(0);
+
+    // A lone CTA of this kernel takes ~22 us (ncu, profiles/): its time is a chain of HBM round trips, not bandwidth.
+    // So the whole M tile (with halo) is requested into L2 up front -- phase 1's register-window stream then pays L2
+    // latency per step -- and likewise what phase 3 will read (R0 under the tile, R1 around it), which travels from
+    // HBM while phases 1-2 run.
+    const void* R0 = nullptr;
+    const void* R1 = nullptr;
+    if (a.Mout) {
+        R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
+        R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
+    }
+    if (RH && use_maps) {
+        if (tid == 0) {
+            prefetch_l2_box(&maps.g, x0 - C::HALO, y0 - MH, 0, p);
+            prefetch_l2_box(&maps.hh, x0 - C::HALO, y0 - MH, 0, p);
+            if (a.Mout) {
+                prefetch_l2_box(&maps.r0, 0, x0 / 32, y0, ring_slot(a.slot0, p, a.nslots));
+                prefetch_l2_box(&maps.r1, 0, x0 / 32 - 1, y0 - 2, ring_slot(a.slot0, p + 1, a.nslots));
+            }
+        }
+    } else {
+        prefetch_m_tile<RH, MH, C::HALO, TH>(Mv, pitch, w, h, x0, y0, tid, NT);
+        if (a.Mout) prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, NT);
+    }
+
+    BF_TRACE_STAMP(1);
+    // ---------------- phase 1: vertical sums ----------------
+    // Column groups are aligned to the image origin: a group is entirely inside the image, entirely left of it, entirely
+    // right of it, or the one group that straddles the right edge (column_task).
+    const bool rows_in = (y0 - MH >= 0) && (y0 + TH + MH <= h);      // block-uniform: no row clamping needed
+    for (int task = tid; task < C::NTASK; task += NT) {
+        if constexpr (RH) {
+            if (task < 3 * C::NC4) {
+                const int c = task / C::NC4, q = task - c * C::NC4;
+                column_task<MH, TH, C::PF, RowH4>(Mv.gplane(c), pitch, w, h, x0 - C::HALO + 4 * q, y0, rows_in,
+                                                  V + (size_t)c * TH * C::VP + 4 * q, C::VP);
+            } else {
+                const int t2 = task - 3 * C::NC4;
+                const int c = t2 / C::NC2, q = t2 - c * C::NC2;
+                column_task<MH, TH, C::PF, RowF2>(Mv.hplane(c), pitch, w, h, x0 - C::HALO + 2 * q, y0, rows_in,
+                                                  V + (size_t)(3 + c) * TH * C::VP + 2 * q, C::VP);
+            }
+        } else {
+            const int c = task / C::NC4, q = task - c * C::NC4;
+            column_task<MH, TH, C::PF, RowF4>(Mv.p + (size_t)c * plane, pitch, w, h, x0 - C::HALO + 4 * q, y0, rows_in,
+                                              V + (size_t)c * TH * C::VP + 4 * q, C::VP);
+        }
+    }
+    __syncthreads();
+    BF_TRACE_STAMP(2);
+
+    // ---------------- phase 2: horizontal sums + solve ----------------
+    const int g = tid & 31, rb = tid >> 5;
+    float2 fl[RG][4];
+#pragma unroll
+    for (int k = 0; k < RG; ++k) {
+        const int r = rb + NW * k;
+        float gs[5][4];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float4* vp = reinterpret_cast<const float4*>(V + ((size_t)c * TH + r) * C::VP) + g;
+            float vv[4 * C::NCH];
+#pragma unroll
+            for (int i = 0; i < C::NCH; ++i) {
+                const float4 t = vp[i];
+                vv[4 * i] = t.x; vv[4 * i + 1] = t.y; vv[4 * i + 2] = t.z; vv[4 * i + 3] = t.w;
+            }
+            // common part vv[D+3 .. D+2MH], summed as two interleaved chains for ILP
+            float t0 = vv[C::D + 3], t1 = vv[C::D + 4];
+#pragma unroll
+            for (int i = C::D + 5; i + 1 <= C::D + 2 * MH; i += 2) { t0 += vv[i]; t1 += vv[i + 1]; }
+            if (((2 * MH - 2) & 1) != 0) t0 += vv[C::D + 2 * MH];
+            const float T = t0 + t1;
+            const float l2 = vv[C::D + 2], l12 = vv[C::D + 1] + l2, l012 = vv[C::D] + l12;
+            const float r1 = vv[C::D + 2 * MH + 1], r12 = r1 + vv[C::D + 2 * MH + 2], r123 = r12 + vv[C::D + 2 * MH + 3];
+            gs[c][0] = T + l012;
+            gs[c][1] = (T + l12) + r1;
+            gs[c][2] = (T + l2) + r12;
+            gs[c][3] = T + r123;
+        }
+        solve4<RH>(gs, reg, fl[k]);
+    }
+    __syncthreads();                                    // all reads of V done before F overwrites it
+#pragma unroll
+    for (int k = 0; k < RG; ++k) {
+        float4* fp = reinterpret_cast<float4*>(F + (rb + NW * k) * kFbTW + 4 * g);
+        fp[0] = make_float4(fl[k][0].x, fl[k][0].y, fl[k][1].x, fl[k][1].y);
+        fp[1] = make_float4(fl[k][2].x, fl[k][2].y, fl[k][3].x, fl[k][3].y);
+    }
+    __syncthreads();
+    BF_TRACE_STAMP(3);
+
+    // ---------------- phase 3: coalesced tail ----------------
+    tile_tail<RH, TH>(a, F, s_red, R0, R1, x0, y0, p, tp.by * nbx + tp.bx, nbx * nby);
+#ifdef BF_TRACE
+    __syncthreads();
+    BF_TRACE_STAMP(4);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_blur_solve_gauss<MH>: the same fused iteration for OPTFLOW_FARNEBACK_GAUSSIAN (separable float32
+// Gaussian window, sigma = 0.3*MH, replicate borders) -- config C4 runs winsize 21 (MH = 10).  No running sums here:
+// every output is a (2MH+1)-tap weighted sum.  Phase 1 walks one scalar column per thread with the (2MH+1)-row window in
+// registers (fully unrolled static ring); phase 2 reads 4+2MH values per channel with LDS.128 and evaluates 4 outputs;
+// summation order is cv2's: centre tap first, then symmetric pairs (x[-i] + x[+i]) * ker[i].
+// ---------------------------------------------------------------------------------------------------
+template <int MH, int TH>
+struct FastGaussCfg {
+    static constexpr int HALO = (MH + 3) / 4 * 4;
+    static constexpr int D = HALO - MH;
+    static constexpr int NCOL = kFbTW + 2 * HALO;
+    static constexpr int VP = NCOL + 4;
+    static constexpr int WIN = 2 * MH + 1;
+    static constexpr int NCH = (D + 2 * MH + 3) / 4 + 1;
+    static constexpr int RG = TH / 8;
+    static constexpr int V_FLOATS = 5 * TH * VP;
+    static constexpr size_t SMEM = (size_t)(V_FLOATS + 64) * sizeof(float);
+    static constexpr int CTAS_SMEM = (int)((227u * 1024u) / (SMEM + 1024u));
+    static constexpr int CTAS_REG = WIN <= 23 ? 3 : 2;
+    static constexpr int CTAS = CTAS_REG < CTAS_SMEM ? CTAS_REG : (CTAS_SMEM < 1 ? 1 : CTAS_SMEM);
+    static_assert(MH >= 2 && MH <= 16, "half window out of range for the fast path");
+    static_assert(TH % 8 == 0, "tile height must be a multiple of 8");
+    static_assert((size_t)TH * kFbTW * sizeof(float2) <= (size_t)V_FLOATS * sizeof(float), "F must fit in V");
+};
+
+template <int MH, bool RH, int TH>
+__global__ void __launch_bounds__(256, FastGaussCfg<MH, TH>::CTAS) k_blur_solve_gauss(const BlurSolveArgs a, const WinCoef wc) {
+    using C = FastGaussCfg<MH, TH>;
+    extern __shared__ __align__(16) float smem[];
+    float* V = smem;
+    float2* F = reinterpret_cast<float2*>(smem);
+    float* s_red = smem + C::V_FLOATS;
+    const int tid = threadIdx.x;
+    const int w = a.w, h = a.h;
+    const int nbx = (w + kFbTW - 1) / kFbTW, nby = (h + TH - 1) / TH;
+    const TilePos tp = decode_cta(blockIdx.x, nbx, nby, a.np, a.pair_group);
+    const int x0 = tp.bx * kFbTW, y0 = tp.by * TH, p = tp.p;
+    const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
+    const MView<RH> Mv(const_cast<void*>(a.M), a.m_stride, p, plane);
+    float ker[MH + 1];
+#pragma unroll
+    for (int i = 0; i <= MH; ++i) ker[i] = wc.ker[i];
+
+    const void* R0 = nullptr;
+    const void* R1 = nullptr;
+    if (a.Mout) {
+        R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
+        R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
+        prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, 256);
+    }
+
+    // ---------------- phase 1: vertical Gaussian, one scalar column per task ----------------
+    for (int task = tid; task < 5 * C::NCOL; task += 256) {
+        const int c = task / C::NCOL, col = task - c * C::NCOL;
+        const int gx = min(max(x0 - C::HALO + col, 0), w - 1);
+        float* dst = V + (size_t)c * TH * C::VP + col;
+        auto ld = [&](int i) -> float {                               // row y0 - MH + i, clamped (replicate)
+            const int r = min(max(y0 - MH + i, 0), h - 1);
+            return Mv.load(c, (unsigned)r * pitch + (unsigned)gx);
+        };
+        float win[C::WIN];
+#pragma unroll
+        for (int i = 0; i < C::WIN; ++i) win[i] = ld(i);
+#pragma unroll
+        for (int j = 0; j < TH; ++j) {
+            // window of output row j: ring slots (j + k) % WIN for k = 0 .. 2MH, centre k = MH
+            float sacc = win[(j + MH) % C::WIN] * ker[0];
+#pragma unroll
+            for (int i = 1; i <= MH; ++i) sacc += (win[(j + MH - i) % C::WIN] + win[(j + MH + i) % C::WIN]) * ker[i];
+            dst[j * C::VP] = sacc;
+            if (j + 1 < TH) win[j % C::WIN] = ld(j + C::WIN);         // row leaving the window is replaced by the next one
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: horizontal Gaussian + solve ----------------
+    const int g = tid & 31, rb = tid >> 5;
+    float2 fl[C::RG][4];
+#pragma unroll
+    for (int k = 0; k < C::RG; ++k) {
+        const int r = rb + 8 * k;
+        float gs[5][4];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float4* vp = reinterpret_cast<const float4*>(V + ((size_t)c * TH + r) * C::VP) + g;
+            float vv[4 * C::NCH];
+#pragma unroll
+            for (int i = 0; i < C::NCH; ++i) {
+                const float4 q4 = vp[i];
+                vv[4 * i] = q4.x; vv[4 * i + 1] = q4.y; vv[4 * i + 2] = q4.z; vv[4 * i + 3] = q4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = C::HALO + j;
+                float sacc = vv[ci] * ker[0];
+#pragma unroll
+                for (int i = 1; i <= MH; ++i) sacc += (vv[ci - i] + vv[ci + i]) * ker[i];
+                gs[c][j] = sacc;
+            }
+        }
+        solve4<RH>(gs, 1e-3f, fl[k]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < C::RG; ++k) {
+        float4* fp = reinterpret_cast<float4*>(F + (rb + 8 * k) * kFbTW + 4 * g);
+        fp[0] = make_float4(fl[k][0].x, fl[k][0].y, fl[k][1].x, fl[k][1].y);
+        fp[1] = make_float4(fl[k][2].x, fl[k][2].y, fl[k][3].x, fl[k][3].y);
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: coalesced tail (same as the box kernel) ----------------
+    tile_tail<RH, TH>(a, F, s_red, R0, R1, x0, y0, p, tp.by * nbx + tp.bx, nbx * nby);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- dispatch ---------------------------------------------------------------------------------------------------------
+// Half windows with a compile-time kernel: box 2..16 (winsize 4..33), Gaussian 2..16.  Tile height: compact plans 16 rows
+// (47 KB shared, 64 registers at winsize 15 -> 4 CTAs/SM: the kernel is latency/issue-bound, resident warps win over the
+// extra vertical halo); exact plans (float4 window rows) 32 rows.  The Gaussian kernel runs 24-row tiles.
+constexpr int kBoxThCompact = 16, kBoxThExact = 32, kGaussTh = 24;
+inline int box_tile_th(bool r_half) { return r_half ? kBoxThCompact : kBoxThExact; }
+inline bool box_fast_supported(const WinCoef& wc, int pitch) { return !wc.gauss && wc.m >= 2 && wc.m <= 16 && (pitch % 4) == 0; }
+inline bool gauss_fast_supported(const WinCoef& wc) { return wc.gauss && wc.m >= 2 && wc.m <= 16; }
+// + at least one 4-column group and two rows (the clamped gather footprint); the row pitch (a multiple of 4 elements,
+// checked above) covers the last group when the width is not a multiple of 4
+inline bool tile_fast_shape(int w, int h) { return w >= 4 && h >= 2; }
+inline bool tile_fast_aligned(const BlurSolveArgs& a) {
+    return aligned16(a.M) && (a.plane_stride % 4) == 0 && (a.m_stride % 16) == 0 && tile_fast_shape(a.w, a.h);
+}
+inline int box_fast_ncta(int w, int h, bool r_half) {
+    const int th = box_tile_th(r_half);
+    return ((w + kFbTW - 1) / kFbTW) * ((h + th - 1) / th);
+}
+inline int gauss_fast_ncta(int w, int h) { return ((w + kFbTW - 1) / kFbTW) * ((h + kGaussTh - 1) / kGaussTh); }
+
+// One launcher per (half window, storage); the instantiations live in tile_inst_*.cu so that they compile in parallel.
+template <int MH, bool RH>
+void launch_box_mh(const BlurSolveArgs& a, float reg, int np, const TileMaps* maps, cudaStream_t st);
+template <int MH, bool RH>
+void launch_gauss_mh(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st);
+
+#ifdef BF_TILE_INSTANTIATE
+// true the first time a (kernel, device) pair is seen: the opt-in shared-memory size is a per-device function attribute
+template <int KEY>
+inline bool smem_attr_needed() {
+    static unsigned long long seen = 0;                 // bit per device ordinal (< 64)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+template <int MH, bool RH>
+void launch_box_mh(const BlurSolveArgs& a, float reg, int np, const TileMaps* maps, cudaStream_t st) {
+    constexpr int TH = RH ? kBoxThCompact : kBoxThExact;
+    using C = FastBoxCfg<MH, TH, RH>;
+    if (smem_attr_needed<MH * 4 + (RH ? 1 : 0)>())       // once per device; a failure would surface at the launch below
+        cudaFuncSetAttribute(k_blur_solve_box<MH, RH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    const unsigned g = (unsigned)(((a.w + kFbTW - 1) / kFbTW) * ((a.h + TH - 1) / TH)) * (unsigned)np;
+    static const TileMaps none{};
+    k_blur_solve_box<MH, RH, TH><<<g, 256, C::SMEM, st>>>(a, reg, maps != nullptr, maps ? *maps : none);
+}
+template <int MH, bool RH>
+void launch_gauss_mh(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
+    using C = FastGaussCfg<MH, kGaussTh>;
+    if (smem_attr_needed<MH * 4 + 2 + (RH ? 1 : 0)>())
+        cudaFuncSetAttribute(k_blur_solve_gauss<MH, RH, kGaussTh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    const unsigned g = (unsigned)(((a.w + kFbTW - 1) / kFbTW) * ((a.h + kGaussTh - 1) / kGaussTh)) * (unsigned)np;
+    k_blur_solve_gauss<MH, RH, kGaussTh><<<g, 256, C::SMEM, st>>>(a, wc);
+}
+#define BF_INSTANTIATE_TILE_MH(MH)                                                                             \
+    template void launch_box_mh<MH, true>(const BlurSolveArgs&, float, int, const TileMaps*, cudaStream_t);    \
+    template void launch_box_mh<MH, false>(const BlurSolveArgs&, float, int, const TileMaps*, cudaStream_t);   \
+    template void launch_gauss_mh<MH, true>(const BlurSolveArgs&, const WinCoef&, int, cudaStream_t);          \
+    template void launch_gauss_mh<MH, false>(const BlurSolveArgs&, const WinCoef&, int, cudaStream_t);
+#endif
+
+#ifndef BF_TILE_INSTANTIATE
+template <bool RH>
+inline void launch_box_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, const TileMaps* maps, cudaStream_t st) {
+    const float reg = 1e-3f / (wc.scale * wc.scale);
+    switch (wc.m) {
+#define BF_CASE(MH) case MH: launch_box_mh<MH, RH>(a, reg, np, maps, st); break;
+        BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8) BF_CASE(9) BF_CASE(10) BF_CASE(11)
+        BF_CASE(12) BF_CASE(13) BF_CASE(14) BF_CASE(15) BF_CASE(16)
+#undef BF_CASE
+        default: break;
+    }
+}
+// maps (optional): tensor maps of this scale, encoded for this window and tile height (compact plans only).
+inline void launch_box_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st, const TileMaps* maps = nullptr) {
+    if (r_half) launch_box_fast_t<true>(a, wc, np, maps, st);
+    else launch_box_fast_t<false>(a, wc, np, nullptr, st);
+}
+template <bool RH>
+inline void launch_gauss_fast_t(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
+    switch (wc.m) {
+#define BF_CASE(MH) case MH: launch_gauss_mh<MH, RH>(a, wc, np, st); break;
+        BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8) BF_CASE(9) BF_CASE(10) BF_CASE(11)
+        BF_CASE(12) BF_CASE(13) BF_CASE(14) BF_CASE(15) BF_CASE(16)
+#undef BF_CASE
+        default: break;
+    }
+}
+inline void launch_gauss_fast(const BlurSolveArgs& a, const WinCoef& wc, int np, bool r_half, cudaStream_t st) {
+    if (r_half) launch_gauss_fast_t<true>(a, wc, np, st);
+    else launch_gauss_fast_t<false>(a, wc, np, st);
+}
+
+#endif  // !BF_TILE_INSTANTIATE
+
+// Host side: encode the tensor maps of one scale (compact plans) for half window mh and tile height th.  M: G planes fp16
+// [pair][3][h][pitch] followed by h planes fp32 [2][h][pitch] (14 * plane bytes per pair); R: packed pixels [slot][h][pitch]
+// x 16 B.  Returns false (maps unused, per-line prefetch instead) if the driver entry point is missing or rejects the layout.
+inline bool encode_tile_maps(TileMaps* out, const void* M, const void* R, int w, int h, int pitch, size_t plane, int max_pairs,
+                             int nslots, int mh, int th) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    if (!encode || w < 4 || h < 2 || pitch % 32 != 0) return false;
+    const int halo = (mh + 3) / 4 * 4;
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    const cuuint64_t pair_bytes = (cuuint64_t)plane * 14;
+    const cuuint32_t bw = (cuuint32_t)(kFbTW + 2 * halo), bh = (cuuint32_t)(th + 2 * mh);
+    if (bw > 256 || bh > 256) return false;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, 3, (cuuint64_t)max_pairs};
+        const cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)plane * 2, pair_bytes};
+        const cuuint32_t box[4] = {bw, bh, 3, 1};
+        if (encode(&out->g, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(M), dims, strides, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, 2, (cuuint64_t)max_pairs};
+        const cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)plane * 4, pair_bytes};
+        const cuuint32_t box[4] = {bw, bh, 2, 1};
+        void* hbase = const_cast<char*>(static_cast<const char*>(M)) + plane * 6;
+        if (encode(&out->hh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hbase, dims, strides, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    // R rows as chunks of 32 pixels (128 words = 512 B): a box row is one long burst, not a 16-byte pixel
+    const cuuint64_t rdims[4] = {128, (cuuint64_t)(pitch / 32), (cuuint64_t)h, (cuuint64_t)nslots};
+    const cuuint64_t rstrides[3] = {512, (cuuint64_t)pitch * 16, (cuuint64_t)plane * 16};
+    const cuuint32_t box0[4] = {128, (cuuint32_t)(kFbTW / 32), (cuuint32_t)th, 1};
+    const cuuint32_t box1[4] = {128, (cuuint32_t)(kFbTW / 32 + 2), (cuuint32_t)(th + 4), 1};
+    if (encode(&out->r0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(R), rdims, rstrides, box0, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (encode(&out->r1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(R), rdims, rstrides, box1, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    return true;
+}
+
+}  // namespace bf

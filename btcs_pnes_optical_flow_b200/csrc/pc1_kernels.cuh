@@ -5,7 +5,10 @@
 //   A  one thread per window: finite mask, mean-centre, covariance, principal axis, align to `ref`
 //      (optical_PCA.py:181-202)
 //   B  one CTA per (cfg, series): compact the valid windows, turn the sequential prev_w sign chain
-//      (optical_PCA.py:203-205) into a prefix product of +-1 over valid windows (block scan)
+//      (optical_PCA.py:203-205) into a block scan over valid windows.  With a_i the ref-aligned axis of window i and s_i
+//      its final sign, the reference tests dot(a_i, s_{i-1} a_{i-1}) < 0: a negative a_i . a_{i-1} flips the running sign,
+//      a positive one keeps it, and an exact ZERO leaves a_i as it is (s_i = +1 whatever came before: a reset).  The
+//      three cases compose associatively as (reset, parity) pairs.
 //   C  one thread per sample: nearest window centre (ties -> later centre, optical_PCA.py:218-225),
 //      non-centred projection (optical_PCA.py:227-233)
 #pragma once
@@ -18,15 +21,18 @@ struct Pc1Cfg {
     int win_n, step_n, K;   // K = number of candidate windows for this configuration
     int win_off;            // offset of this cfg's windows inside the per-series window scratch
 };
+// Window configurations travel as a kernel parameter (no host-to-device copy from pageable memory in a stream-ordered call).
+constexpr int kPc1MaxCfg = 32;
+struct Pc1CfgPack { Pc1Cfg c[kPc1MaxCfg]; };
 
 // scratch per (cfg, series): wx[Ktot], wy[Ktot] (aligned axis or compacted+signed axis), cen[Ktot], nvalid
 __global__ void k_pc1_windows(const double* __restrict__ vx, const double* __restrict__ vy, int n_series, int n,
-                              const Pc1Cfg* __restrict__ cfgs, int n_cfg, int Ktot, double ref_x, double ref_y,
+                              const Pc1CfgPack cfgs, int n_cfg, int Ktot, double ref_x, double ref_y,
                               int min_samples, double* __restrict__ wx, double* __restrict__ wy,
                               int* __restrict__ valid) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y, c = blockIdx.z;
-    const Pc1Cfg cf = cfgs[c];
+    const Pc1Cfg cf = cfgs.c[c];
     if (j >= cf.K) return;
     const double* x = vx + (size_t)s * n;
     const double* y = vy + (size_t)s * n;
@@ -79,12 +85,12 @@ __device__ __forceinline__ int block_excl_scan_add(int v, int* sh, int* total) {
 
 // Phase B.  In place: on exit the first nvalid entries of wx/wy/cen hold the signed axes and centres of
 // the valid windows in order; nvalid_out[(s, c)] = count.
-__global__ void k_pc1_chain(const Pc1Cfg* __restrict__ cfgs, int n_cfg, int Ktot, double* __restrict__ wx,
+__global__ void k_pc1_chain(const Pc1CfgPack cfgs, int n_cfg, int Ktot, double* __restrict__ wx,
                             double* __restrict__ wy, const int* __restrict__ valid, double* __restrict__ cwx,
                             double* __restrict__ cwy, int* __restrict__ cen, int* __restrict__ nvalid_out) {
     extern __shared__ int sh[];
     const int s = blockIdx.x, c = blockIdx.y;
-    const Pc1Cfg cf = cfgs[c];
+    const Pc1Cfg cf = cfgs.c[c];
     const size_t base = (size_t)s * Ktot + cf.win_off;
     const int t = threadIdx.x, nt = blockDim.x;
     const int per = (cf.K + nt - 1) / nt;
@@ -104,37 +110,55 @@ __global__ void k_pc1_chain(const Pc1Cfg* __restrict__ cfgs, int n_cfg, int Ktot
     }
     __syncthreads();
     if (t == 0) nvalid_out[s * n_cfg + c] = total;
-    // 2) sign chain over the compacted axes: flips_i = [a_i . a_{i-1} < 0]; s_i = (-1)^(prefix count)
+    // 2) sign chain over the compacted axes.  Step code of window i from d = a_i . a_{i-1}: 0 keep (d > 0), 1 flip (d < 0),
+    //    2 reset (d == 0, or i == 0).  A run of steps composes to (reset << 1 | parity).
     const int per2 = (total + nt - 1) / nt;
     const int lo2 = min(t * per2, total), hi2 = min(lo2 + per2, total);
-    int fl = 0;
-    for (int i = lo2; i < hi2; ++i)
-        if (i > 0 && cwx[base + i] * cwx[base + i - 1] + cwy[base + i] * cwy[base + i - 1] < 0.0) ++fl;
-    int tot2;
-    int run = block_excl_scan_add(fl, sh, &tot2);
-    // the dot products above must all be read before anyone flips an axis
-    // (block_excl_scan_add ends with __syncthreads, and every thread computed its flags before it)
+    auto step_code = [&](int i) -> int {
+        if (i == 0) return 2;
+        const double d = cwx[base + i] * cwx[base + i - 1] + cwy[base + i] * cwy[base + i - 1];
+        return d < 0.0 ? 1 : (d == 0.0 ? 2 : 0);
+    };
+    auto compose = [](int first, int then) -> int { return (then & 2) ? then : ((first & 2) | ((first ^ then) & 1)); };
+    int mine = 0;
+    for (int i = lo2; i < hi2; ++i) mine = compose(mine, step_code(i));
+    // inclusive Hillis-Steele scan with the (non-commutative) composition; every dot product above is read before anyone
+    // flips an axis (the scan's barriers separate the two)
+    sh[t] = mine;
+    __syncthreads();
+    for (int o = 1; o < nt; o <<= 1) {
+        const int prev = (t >= o) ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] = compose(prev, sh[t]);
+        __syncthreads();
+    }
+    int state = (t > 0) ? sh[t - 1] : 0;                 // composite of everything before this thread's run
+    // replay the run: the dots must be taken against the UNFLIPPED neighbours, so read ahead before writing
     double px = 0, py = 0;
-    bool have_prev = false;
-    if (lo2 > 0 && lo2 < hi2) { px = cwx[base + lo2 - 1]; py = cwy[base + lo2 - 1]; have_prev = true; }
+    if (lo2 > 0 && lo2 < hi2) { px = cwx[base + lo2 - 1]; py = cwy[base + lo2 - 1]; }
     __syncthreads();
     for (int i = lo2; i < hi2; ++i) {
         const double ax = cwx[base + i], ay = cwy[base + i];
-        if (have_prev && ax * px + ay * py < 0.0) ++run;
-        px = ax; py = ay; have_prev = true;
-        if (run & 1) { cwx[base + i] = -ax; cwy[base + i] = -ay; }
+        int code = 2;
+        if (i > 0) {
+            const double d = ax * px + ay * py;
+            code = d < 0.0 ? 1 : (d == 0.0 ? 2 : 0);
+        }
+        state = compose(state, code);
+        px = ax; py = ay;
+        if (state & 1) { cwx[base + i] = -ax; cwy[base + i] = -ay; }
     }
 }
 
 // Phase C.
 __global__ void k_pc1_project(const double* __restrict__ vx, const double* __restrict__ vy, int n_series, int n,
-                              const Pc1Cfg* __restrict__ cfgs, int n_cfg, int Ktot, const double* __restrict__ cwx,
+                              const Pc1CfgPack cfgs, int n_cfg, int Ktot, const double* __restrict__ cwx,
                               const double* __restrict__ cwy, const int* __restrict__ cen,
                               const int* __restrict__ nvalid, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y, c = blockIdx.z;
     if (i >= n) return;
-    const Pc1Cfg cf = cfgs[c];
+    const Pc1Cfg cf = cfgs.c[c];
     const size_t base = (size_t)s * Ktot + cf.win_off;
     const int K = nvalid[s * n_cfg + c];
     double r = nan("");

@@ -71,9 +71,22 @@ def sharded_flow_series(compute_chunk: Callable[[int, int], torch.Tensor], T: in
     rows = shard_rows(T, world)
     lo, hi = rows[rank]
     f0, f1 = frames_for_rows(lo, hi)
+    local = None
     if hi > lo:
         chunk = compute_chunk(f0, f1)
         local = chunk[:, 1:]                      # drop the chunk's own NaN row (its first frame has no prev here)
-    else:
-        local = compute_chunk(f0, f0)[:, :0]
+    if world > 1:
+        # A rank without rows (more ranks than pairs) never calls compute_chunk -- in production that would be a flow
+        # series over zero frames -- and takes the shape of its empty chunk from rank 0, which owns rows whenever T > 1.
+        meta = [None]
+        if rank == 0 and local is not None:
+            meta = [(int(local.shape[0]), str(local.dtype).split(".")[-1])]
+        dist.broadcast_object_list(meta, src=0, group=group)
+        if local is None:
+            n_roi, dtype = meta[0] if meta[0] is not None else (1, "float32")
+            backend = dist.get_backend(group)
+            dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+            local = torch.empty((n_roi, 0, 3), dtype=getattr(torch, dtype), device=dev)
+    elif local is None:
+        local = torch.empty((1, 0, 3), dtype=torch.float32)
     return gather_series(local, rows, T, dst, group)

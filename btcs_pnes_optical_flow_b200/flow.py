@@ -68,8 +68,9 @@ class FlowPlan:
 
     def __init__(self, width: int, height: int, params: dict | None = None, max_pairs: int = 8,
                  max_rois: int = 1, device: int | None = None, exact: bool = False):
-        """exact=True keeps the polynomial coefficients as float32 planes (needed for float32 input frames); the
-        default packs them as fp16 for poly_n 5/7 (storage only, <= 5e-4 px against cv2)."""
+        """exact=True keeps polynomial coefficients and matrices as float32 planes (needed for float32 input frames or other
+        poly_n); the default for uint8 frames with poly_n 5/7 is the compact storage (16-byte coefficient pixel, fp16 G +
+        fp32 h matrices: storage only, arithmetic fp32; ~1e-6 px mean against cv2)."""
         self._lib = _lib.load()
         self.params = dict(FB_PARAMS, **(params or {}))
         self.width, self.height = int(width), int(height)
@@ -132,14 +133,21 @@ class FlowPlan:
         return sum(s["w"] * s["h"] for s in self.scales())
 
     def profile(self, enable: bool = True) -> None:
-        """Bracket every finest-scale blur+solve launch with CUDA events (bf_plan_profile)."""
+        """Bracket every stage of the flow calls with tagged CUDA events (bf_plan_profile)."""
         check(self._lib.bf_plan_profile(self._h, int(enable)))
 
     def profile_read(self) -> dict:
-        """Wait for the recorded events: dict(launches, total_ms, pair_iterations); clears the record."""
+        """Wait for the recorded events and clear the record.  dict(launches, total_ms, pair_iterations) of the
+        finest-scale blur+solve launches, plus `stages`: per BF_PROF_* tag (iter_update, iter_last, update, coarse,
+        expand) a dict(launches, ms, pairs)."""
         n, ms, pi = C.c_int(), C.c_double(), C.c_longlong()
         check(self._lib.bf_plan_profile_read(self._h, C.byref(n), C.byref(ms), C.byref(pi)))
-        return dict(launches=n.value, total_ms=ms.value, pair_iterations=pi.value)
+        out = dict(launches=n.value, total_ms=ms.value, pair_iterations=pi.value, stages={})
+        for tag, name in enumerate(_lib.BF_PROF_TAGS):
+            tn, tms, tp = C.c_int(), C.c_double(), C.c_longlong()
+            check(self._lib.bf_plan_profile_tag(self._h, tag, C.byref(tn), C.byref(tms), C.byref(tp)))
+            out["stages"][name] = dict(launches=tn.value, ms=tms.value, pairs=tp.value)
+        return out
 
     # -- one frame pair --------------------------------------------------------------------------------
     def flow_pair(self, prev, nxt, flow=None):
@@ -287,6 +295,14 @@ class PendingSeries:
             if self._T == 1:
                 self._out.fill_(float("nan"))
         return self._out.numpy()
+
+    def __del__(self):
+        # dropped without result(): the queued copies still read the frames and write the pinned result buffer
+        try:
+            if not self._done and getattr(self._plan, "_h", None):
+                self._plan._lib.bf_flow_series_wait(self._plan._h, self._ticket)
+        except Exception:
+            pass
 
 
 def _coerce_pair(prev, nxt, W: int | None = None, H: int | None = None):

@@ -31,6 +31,7 @@ class ClipSpec:
     tau: float = 8.0          # amplitude decay constant (s)
     direction: tuple = (0.6, 0.8)   # unit vector (x, y) of the motion
     center: tuple | None = None     # patch centre (x, y); default frame centre
+    roi2_dx: int = 0                # != 0: a second ROI of the same size, its centre shifted by this many pixels in x
 
     def displacement(self, t: np.ndarray) -> np.ndarray:
         t = np.asarray(t, float)
@@ -53,6 +54,15 @@ class ClipSpec:
         r = self.roi // 2
         m[max(cy - r, 0):cy + r + 1, max(cx - r, 0):cx + r + 1] = True  # inclusive like cv2.fillPoly
         return m
+
+    def roi_masks(self) -> np.ndarray:
+        """[n_roi, H, W] bool: the ROI around the patch and, for two-ROI configurations (C5: bilateral limbs), a second ROI
+        of the same size beside it."""
+        masks = [self.roi_mask()]
+        if self.roi2_dx and self.roi > 0:
+            cx, cy = self.center or (self.W // 2, self.H // 2)
+            masks.append(ClipSpec(H=self.H, W=self.W, roi=self.roi, center=(cx + self.roi2_dx, cy)).roi_mask())
+        return np.stack(masks)
 
 
 def smooth_noise(h: int, w: int, gen: torch.Generator, device, lo: float = 30.0, hi: float = 225.0) -> torch.Tensor:
@@ -120,7 +130,7 @@ def config_spec(name: str, **over) -> tuple[ClipSpec, dict]:
         spec = ClipSpec(T=900, H=480, W=640, fps=30.0, patch=160, roi=200, amp=6.0)
     elif name in ("C2", "C3", "C5"):
         spec = ClipSpec(T=9000 if name == "C2" else 300, H=1080, W=1920, fps=30.0, patch=360, roi=0 if name != "C5" else 440,
-                        amp=8.0)
+                        amp=8.0, center=(700, 540) if name == "C5" else None, roi2_dx=520 if name == "C5" else 0)
     elif name == "C4":
         spec = ClipSpec(T=600, H=2160, W=3840, fps=60.0, patch=720, roi=0, amp=12.0)
         base.update(levels=5, winsize=21, poly_n=7, poly_sigma=1.5, flags=256)

@@ -91,6 +91,21 @@ int bf_plan_scale_info(const bf_plan* plan, int i, int* w, int* h, int* ksize, d
  * they processed (one launch handles a batch of pairs for ONE iteration), then clears the record. */
 int bf_plan_profile(bf_plan* plan, int enable);
 int bf_plan_profile_read(bf_plan* plan, int* n_launches, double* total_ms, long long* pair_iterations);
+/* While profiling is enabled every stage of the series / pair calls is bracketed the same way and tagged:
+ *   BF_PROF_ITER_UPDATE  finest-scale blur + solve + UpdateMatrices launches (read M, R0, gathered R1; write M')
+ *   BF_PROF_ITER_LAST    finest-scale last iteration (blur + solve + projection / ROI sums or dense flow store)
+ *   BF_PROF_UPDATE       finest-scale flow upsample + first UpdateMatrices
+ *   BF_PROF_COARSE       the same three at all coarser scales
+ *   BF_PROF_EXPAND       pyramid + polynomial expansion of the new frames of a batch (all scales)
+ * bf_plan_profile_read (above) returns ITER_UPDATE + ITER_LAST and latches the per-tag sums, which
+ * bf_plan_profile_tag then reports: launches (event pairs), summed device ms, summed pairs (frames for EXPAND). */
+#define BF_PROF_ITER_UPDATE 0
+#define BF_PROF_ITER_LAST 1
+#define BF_PROF_UPDATE 2
+#define BF_PROF_COARSE 3
+#define BF_PROF_EXPAND 4
+#define BF_PROF_NTAGS 5
+int bf_plan_profile_tag(const bf_plan* plan, int tag, int* n_launches, double* total_ms, long long* pairs);
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 long long bf_launch_count(void);
 void bf_launch_count_reset(void);

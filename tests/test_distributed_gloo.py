@@ -57,11 +57,11 @@ def _worker(rank, world, port, frames, masks, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_series_equals_unsharded(world):
+@pytest.mark.parametrize("world,T", [(2, 10), (3, 10), (3, 3)])      # (3, 3): two pairs on three ranks, the last rank has no rows
+def test_sharded_series_equals_unsharded(world, T):
     from btcs_pnes_optical_flow_b200 import synthetic as syn
     from oracle import cv2_ref
-    spec = syn.ClipSpec(T=10, H=64, W=80, seed=1, patch=24, roi=32, amp=2.0)
+    spec = syn.ClipSpec(T=T, H=64, W=80, seed=1, patch=24, roi=32, amp=2.0)
     frames = syn.make_clip_np(spec)
     masks = np.stack([spec.roi_mask(), np.ones((64, 80), bool)])
     ref = cv2_ref.roi_series(frames, [1.0, 0.0], [0.0, 1.0], masks, cv2_ref.FB_PARAMS, threads=1).astype(np.float32)

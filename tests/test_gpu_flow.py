@@ -125,23 +125,20 @@ def test_torch_tensors_stay_on_device():
 
 
 def test_all_kernel_variants_agree(monkeypatch):
-    """The same parameters through the three implementations of the iteration kernel -- tile (default), warp-specialised
-    strip-marching (BTCSFLOW_KERNEL=march), runtime-parameter (BTCSFLOW_NO_FAST=1) -- and both coefficient storage
-    formats, all inside the tight gate against cv2 and within float rounding of each other."""
+    """The same parameters through the implementations of the iteration kernel -- compile-time-window tile kernels
+    (default), runtime-parameter kernel (BTCSFLOW_NO_FAST=1) -- both storage formats and both L2-prefetch flavours, all
+    inside the tight gate against cv2 and within float rounding of each other."""
     import btcs_pnes_optical_flow_b200 as B
     from oracle import cv2_ref
     for (h, w) in ((270, 480), (203, 316)):
         a, b = textured(h, w, 1), textured(h, w, 1, shift=(1.7, -0.8))
-        for p in (B.FB_PARAMS, dict(B.FB_PARAMS, levels=5, winsize=21, poly_n=7, poly_sigma=1.5, flags=256)):
+        for p in (B.FB_PARAMS, dict(B.FB_PARAMS, levels=5, winsize=21, poly_n=7, poly_sigma=1.5, flags=256),
+                  dict(B.FB_PARAMS, winsize=9), dict(B.FB_PARAMS, winsize=25, levels=2), dict(B.FB_PARAMS, winsize=15, flags=256)):
             ref = cv2_ref.farneback(a, b, **p)
             outs = {}
-            for name, env in (("tile", {}), ("march", {"BTCSFLOW_KERNEL": "march"}),
-                              ("tile_f32", {"BTCSFLOW_R_STORAGE": "f32"}),
-                              ("march_f32", {"BTCSFLOW_KERNEL": "march", "BTCSFLOW_R_STORAGE": "f32"}),
+            for name, env in (("tile", {}), ("tile_f32", {"BTCSFLOW_R_STORAGE": "f32"}),
                               ("fused_l0", {"BTCSFLOW_FUSED_L0": "1"}),
-                              ("no_tmap", {"BTCSFLOW_TMAP": "0"}),            # per-row L2 prefetch instead of tensor maps
-                              ("serial_tail", {"BTCSFLOW_TAIL": "serial"}),   # gathers not issued ahead
-                              ("th24", {"BTCSFLOW_TILE_TH": "24"}), ("th32", {"BTCSFLOW_TILE_TH": "32"}),
+                              ("no_tmap", {"BTCSFLOW_TMAP": "0"}),            # per-line L2 prefetch instead of tensor maps
                               ("generic", {"BTCSFLOW_NO_FAST": "1"})):
                 for k, v in env.items():
                     monkeypatch.setenv(k, v)
@@ -150,15 +147,12 @@ def test_all_kernel_variants_agree(monkeypatch):
                 for k in env:
                     monkeypatch.delenv(k)
                 mean, mx = epe(outs[name], ref)
-                assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (name, h, w, mean, mx)
-            assert epe(outs["march_f32"], outs["generic"])[1] < 1e-4 and epe(outs["tile_f32"], outs["generic"])[1] < 1e-4
-            # compact storage (fp16 R and M): both kernels quantise the same values, summation order differs
-            assert epe(outs["march"], outs["generic"])[1] < 2e-3 and epe(outs["tile"], outs["march"])[1] < 1e-3
+                assert mean <= MEAN_TIGHT and mx <= MAX_TIGHT, (name, h, w, p, mean, mx)
+            assert epe(outs["tile_f32"], outs["generic"])[1] < 1e-4
+            # compact storage (packed R, fp16 G + fp32 h): close to the all-fp32 path
+            assert epe(outs["tile"], outs["generic"])[1] < 1e-3, epe(outs["tile"], outs["generic"])
             assert epe(outs["fused_l0"], outs["tile"])[1] < 1e-3        # level-0 blur fused into the expansion (opt-in)
-            # prefetch flavour and gather scheduling do not touch the arithmetic; tile height only moves where the
-            # running vertical sums restart
-            assert np.array_equal(outs["no_tmap"], outs["tile"]) and np.array_equal(outs["serial_tail"], outs["tile"])
-            assert epe(outs["th24"], outs["tile"])[1] < 1e-3 and epe(outs["th32"], outs["tile"])[1] < 1e-3
+            assert np.array_equal(outs["no_tmap"], outs["tile"])        # the prefetch flavour does not touch the arithmetic
 
 
 def test_widths_not_multiple_of_4(monkeypatch):
@@ -210,11 +204,61 @@ def test_4k_gaussian_config_full_size():
     # float32 storage: the whole frame, borders included
     mean, mx = epe(got_exact, ref)
     assert mean <= 1e-4 and mx <= MAX_TIGHT, (mean, mx)
-    # compact storage: tight on the interior and the mean; a moving texture can flip the `inside` branch of a pixel in the
-    # last column (seen: 80 px around (3839, 1473), 0.056 px), which the 21-px window spreads over the border band
+    # compact storage (fp16 G + consistently rounded fp32 h, packed R): the north_star gate on the WHOLE frame, border band
+    # included (the all-fp16 matrices of round 1 flipped the `inside` branch of ~80 last-column pixels here: 0.056 px)
     mean, inner_mx, band_mx = epe_banded(got, ref, 32)
-    assert mean <= MEAN_TIGHT and inner_mx <= MAX_TIGHT and band_mx <= 0.25, (mean, inner_mx, band_mx)
-    d = np.sqrt(((got - ref) ** 2).sum(-1))
-    assert (d > MAX_TIGHT).mean() < 1e-4
+    assert mean <= 1e-4 and inner_mx <= MAX_TIGHT and band_mx <= MAX_GATE, (mean, inner_mx, band_mx)
     inner = got[200:-200, 200:-200]
     assert abs(inner[..., 0].mean() - 3.4) < 0.05 and abs(inner[..., 1].mean() + 2.2) < 0.05
+
+
+def test_static_border_band_is_the_same_on_the_exact_plan():
+    """GPU side of tests/test_oracle_farneback.py::test_static_border_branch_flip_is_inherent: on the static-border clip the
+    EXACT plan (everything fp32, ~1e-6 px on the interior) shows the same > 0.05 px band against cv2 as the NumPy
+    restatement does -- the band is a property of the reference's branch on a numerically-zero flow, not of a storage
+    format -- and the compact plan's band is no worse than the exact plan's."""
+    import btcs_pnes_optical_flow_b200 as B
+    from btcs_pnes_optical_flow_b200 import synthetic as syn
+    from oracle import cv2_ref, farneback_np
+    spec = syn.ClipSpec(T=2, H=480, W=640, seed=0, patch=160, roi=200, amp=6.0)
+    fr = syn.make_clip_np(spec, 3, 2)
+    ref = cv2_ref.farneback(fr[0], fr[1], **B.FB_PARAMS)
+    ora = farneback_np.farneback(fr[0], fr[1], **B.FB_PARAMS)
+    res = {}
+    for kind in ("exact", "compact"):
+        with B.FlowPlan(640, 480, B.FB_PARAMS, exact=(kind == "exact")) as plan:
+            got = plan.flow_pair(fr[0], fr[1])
+        mean, inner, band = epe_banded(got, ref, 16)
+        res[kind] = (mean, inner, band)
+        assert inner <= (1e-4 if kind == "exact" else MAX_TIGHT) and mean <= MEAN_TIGHT, (kind, mean, inner, band)
+        assert band <= 0.25, (kind, band)
+        m = spec.roi_mask()
+        assert abs(got[m].mean(0) - ref[m].mean(0)).max() < 1e-4            # what the reference consumes
+    assert epe_banded(ora, ref, 16)[2] > 0.05                                # the faithful restatement breaks the gate there too
+    assert res["compact"][2] <= max(2.0 * res["exact"][2], 0.1), res
+
+
+def test_sharp_edges_large_shifts_stay_finite():
+    """Binary blocks / text-like patterns shifted by 30-80 px: the h terms of M reach ~4e4 (an all-fp16 M overflowed towards
+    inf -> NaN in the box sums).  Compact plans keep h in fp32 and saturate G: output finite and inside the gate vs cv2."""
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    rng = np.random.default_rng(5)
+    h, w = 240, 416
+    base = np.zeros((h + 200, w + 200), np.uint8)
+    for _ in range(220):                                                      # white rectangles on black: sharpest possible edges
+        y, x = int(rng.integers(0, h + 180)), int(rng.integers(0, w + 180))
+        base[y:y + int(rng.integers(3, 24)), x:x + int(rng.integers(3, 40))] = 255
+    for shift in ((30, 0), (47, -33), (80, 12)):
+        a = np.ascontiguousarray(base[100:100 + h, 100:100 + w])
+        b = np.ascontiguousarray(base[100 - shift[1]:100 - shift[1] + h, 100 - shift[0]:100 - shift[0] + w])
+        ref = cv2_ref.farneback(a, b, **B.FB_PARAMS)
+        with B.FlowPlan(w, h, B.FB_PARAMS, max_rois=1) as plan:
+            got = plan.flow_pair(a, b)
+            rows = plan.flow_series(np.stack([a, b]), None, None, np.ones((h, w), bool))[0]
+        assert np.isfinite(got).all() and np.isfinite(rows[1]).all(), shift
+        mean, inner, band = epe_banded(got, ref, 16)
+        # ill-conditioned content (aperture problem on straight edges, flows of hundreds of px in cv2 itself): the gate is held
+        # on the mean and on the bulk of the pixels
+        d = np.sqrt(((got - ref) ** 2).sum(-1))
+        assert mean <= MEAN_GATE and (d > MAX_GATE).mean() < 5e-3, (shift, mean, inner, band, (d > MAX_GATE).mean())

@@ -163,3 +163,35 @@ def test_cli_pca_command_matches_reference_pipeline(tmp_path, golden):
     assert list(df.columns) == ["t_sec", "pc1_dyn"]
     got, ref = df["pc1_dyn"].to_numpy(), g["pc1"]
     assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.nanmax(np.abs(got - ref)) < 1e-10
+
+
+def test_pc1_zero_dot_resets_the_sign_chain():
+    """optical_PCA.py:203-205 flips a window's axis only when dot(w, prev_w) < 0.  When the dot is exactly 0 -- axis-aligned
+    windows [1, 0] next to [0, 1], reachable when one component is constant in a window -- the reference keeps w as aligned
+    to `ref`, whatever sign the chain carried.  (A prefix product of signs inherits the previous sign there.)"""
+    from btcs_pnes_optical_flow_b200 import pca
+    from oracle import pc1_np
+    n, win_n, step_n = 200, 10, 10
+    t = np.arange(n, dtype=float)
+    osc = np.sin(0.9 * t)
+    vx, vy = np.zeros(n), np.zeros(n)
+    # windows (10 samples each): A) motion along (1, -1): aligned to ref=(0,1) it becomes (-1, 1)/sqrt2;
+    # B) motion along x only -> sxy == 0 -> axis [1, 0], dot with A's signed axis < 0 -> flipped to [-1, 0] (chain sign -1);
+    # C) motion along y only -> axis [0, 1]: dot with [-1, 0] is exactly 0 -> NOT flipped in the reference;
+    # D) along x again, dot with [0, 1] exactly 0 -> stays [+1, 0]
+    for k in range(0, n // win_n):
+        s = slice(k * win_n, (k + 1) * win_n)
+        kind = k % 4
+        if kind == 0:
+            vx[s], vy[s] = osc[s], -osc[s]
+        elif kind == 1:
+            vx[s] = osc[s]
+        elif kind == 2:
+            vy[s] = osc[s]
+        else:
+            vx[s] = osc[s]
+    want = pc1_np.dynamic_pc1_sliding(vx, vy, win_n, step_n)
+    got = pca.pc1_sliding_batched(vx[None], vy[None], [win_n], [step_n])[0, 0]
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.nanmax(np.abs(got - want)) < 1e-12, np.nanmax(np.abs(got - want))
+    assert np.abs(want).max() > 0.5

@@ -45,7 +45,6 @@ def test_series_batching_multi_roi_and_device_api():
         assert np.nanmax(np.abs(out[:2] - ref)) < 5e-4
         assert np.isnan(out[2]).all()                                             # empty ROI -> NaN like np.nanmean
         # dense flow of pair t equals the stand-alone pair call
-        # (3 ROIs take the tile kernel for the last iteration, the pair call the marching kernel: float rounding apart)
         assert np.abs(flow[4] - B.calcOpticalFlowFarneback(fr[4], fr[5], None, **B.FB_PARAMS)).max() < 1e-5
         dev = plan.flow_series(torch.from_numpy(fr).cuda(), None, None, torch.from_numpy(masks).cuda())
         assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), out, equal_nan=True)   # host path == device path
@@ -151,3 +150,65 @@ def test_async_host_series_matches_sync():
         one = plan.flow_series_async(pa[:1], None, None, mask).result()
     assert np.array_equal(got_a, want_a, equal_nan=True) and np.array_equal(got_b, want_b, equal_nan=True)
     assert one.shape == (1, 1, 3) and np.isnan(one).all()
+
+
+def test_c2_full_size_series_batch_of_64_with_ring_wrap():
+    """Config C2 as bench.py runs it: 1080p, 64 pairs per launch, a series longer than one batch (the frame ring wraps),
+    full-frame ROI -- every row against cv2 on the same frames, and the dense field of pairs taken from inside a batch."""
+    import torch
+    import btcs_pnes_optical_flow_b200 as B
+    from btcs_pnes_optical_flow_b200 import synthetic as syn
+    from oracle import cv2_ref
+    spec, p = syn.config_spec("C2")
+    T = 72
+    spec.T = T
+    fr = syn.make_clip(spec, "cuda", 0, T)
+    fr_h = fr.cpu().numpy()
+    check = [1, 2, 33, 63, 64, 65, 66, 71]                                     # both sides of the batch boundary (pair 64 = ring slot 0)
+    with B.FlowPlan(spec.W, spec.H, p, max_pairs=64, max_rois=1) as plan:
+        rows = plan.flow_series(fr, None, None, torch.from_numpy(spec.roi_mask()).cuda()).cpu().numpy()[0]
+        _, flow = plan.flow_series(fr[:66], None, None, torch.from_numpy(spec.roi_mask()).cuda(), return_flow=True)
+        dense = {k: flow[k].cpu().numpy() for k in (7, 40, 64)}
+        del flow
+    assert np.isnan(rows[0]).all() and np.isfinite(rows[1:]).all()
+    mask = spec.roi_mask()
+    for t in check:
+        want = cv2_ref.roi_mean_body_flow(fr_h[t - 1], fr_h[t], [1.0, 0.0], [0.0, 1.0], mask, p)
+        assert np.abs(rows[t] - np.asarray(want)).max() < 5e-4, (t, rows[t], want)
+    from tests.helpers import epe_banded
+    for k, got in dense.items():
+        ref = cv2_ref.farneback(fr_h[k], fr_h[k + 1], **p)
+        mean, inner, band = epe_banded(got, ref, 16)
+        assert mean <= 1e-3 and inner <= 5e-3 and band <= 0.25, (k, mean, inner, band)   # static border: band bounded (DESIGN 2)
+
+
+def test_c5_two_rois_full_size():
+    """Config C5: 1080p, two ROIs, rows of both against cv2; the window sweep runs in one batched PC1 call."""
+    import torch
+    import btcs_pnes_optical_flow_b200 as B
+    from btcs_pnes_optical_flow_b200 import pca, synthetic as syn
+    from oracle import cv2_ref, pc1_np
+    spec, p = syn.config_spec("C5")
+    T = 20
+    spec.T = T
+    fr = syn.make_clip(spec, "cuda", 0, T)
+    fr_h = fr.cpu().numpy()
+    masks = spec.roi_masks()
+    assert masks.shape[0] == 2 and masks[0].sum() == masks[1].sum() > 0 and not (masks[0] & masks[1]).any()
+    with B.FlowPlan(spec.W, spec.H, p, max_pairs=8, max_rois=2) as plan:
+        rows = plan.flow_series(fr, None, None, torch.from_numpy(masks).cuda())
+        ref = cv2_ref.roi_series(fr_h, [1.0, 0.0], [0.0, 1.0], masks, p, threads=8)
+        got = rows.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.nanmax(np.abs(got - ref)) < 5e-4, np.nanmax(np.abs(got - ref))
+        assert np.abs(ref[0, 1:, 2]).mean() > 10 * np.abs(ref[1, 1:, 2]).mean()          # ROI 0 holds the moving patch, ROI 1 background
+    # the sweep: 2 ROIs x 4 windows in one call equals the sequential oracle per (ROI, window)
+    n = 400
+    t = np.arange(n) / 30.0
+    vx = np.stack([np.sin(2 * np.pi * 3 * t) * 0.6, np.cos(2 * np.pi * 2 * t) * 0.3])
+    vy = np.stack([np.sin(2 * np.pi * 3 * t + 0.2) * 0.8, np.sin(2 * np.pi * 2 * t) * 0.5])
+    wins = [pc1_np.window_samples(w, 0.1, 30) for w in (0.5, 1.0, 2.0, 4.0)]
+    out = pca.pc1_sliding_batched(vx, vy, [w for w, _ in wins], [s for _, s in wins])
+    for c, (wn, sn) in enumerate(wins):
+        for r in range(2):
+            want = pc1_np.dynamic_pc1_sliding(vx[r], vy[r], wn, sn)
+            assert np.array_equal(np.isnan(out[c, r]), np.isnan(want)) and np.nanmax(np.abs(out[c, r] - want)) < 1e-11

@@ -24,7 +24,6 @@ P = dict(B.FB_PARAMS)
 G = dict(B.FB_PARAMS, levels=5, winsize=21, poly_n=7, poly_sigma=1.5, flags=256)
 run("tile", {}, P)
 run("tile_w4", {}, P, shape=(135, 240))
-run("march", {"BTCSFLOW_KERNEL": "march"}, P)
 run("tile_f32", {"BTCSFLOW_R_STORAGE": "f32"}, P)
 run("exact", {}, P, exact=True)
 run("generic", {"BTCSFLOW_NO_FAST": "1"}, P)
