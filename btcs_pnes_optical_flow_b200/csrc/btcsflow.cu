@@ -191,6 +191,23 @@ bool make_poly_coef(int n, double sigma, bf::PolyCoef& pc) {
     return true;
 }
 
+// cv2.resize INTER_AREA coefficient table for one axis (computeResizeAreaTab), CSR form
+void area_table(int ssize, int dsize, std::vector<int>& ofs, std::vector<int>& idx, std::vector<float>& wgt) {
+    const double scale = (double)ssize / dsize;
+    ofs.assign(1, 0); idx.clear(); wgt.clear();
+    for (int d = 0; d < dsize; ++d) {
+        if (ssize == dsize) { idx.push_back(d); wgt.push_back(1.f); ofs.push_back((int)idx.size()); continue; }
+        const double f1 = d * scale, f2 = f1 + scale, cell = std::min(scale, ssize - f1);
+        int s1 = (int)std::ceil(f1), s2 = (int)std::floor(f2);
+        s2 = std::min(s2, ssize - 1);
+        s1 = std::min(s1, s2);
+        if (s1 - f1 > 1e-3) { idx.push_back(s1 - 1); wgt.push_back((float)((s1 - f1) / cell)); }
+        for (int sx = s1; sx < s2; ++sx) { idx.push_back(sx); wgt.push_back((float)(1.0 / cell)); }
+        if (f2 - s2 > 1e-3) { idx.push_back(s2); wgt.push_back((float)(std::min(std::min(f2 - s2, 1.0), cell) / cell)); }
+        ofs.push_back((int)idx.size());
+    }
+}
+
 void make_win_coef(int winsize, int flags, bf::WinCoef& wc) {
     const int m = winsize / 2;
     wc.m = m;
@@ -233,8 +250,8 @@ struct ScaleInfo {
     float* tmpk = nullptr;                    // horizontal-pass scratch of this level [F][H][pitch] (levels coarser than 0)
     void* R = nullptr;                        // fp32 planes [F][5][h][pitch], or packed fp16 pixels [F][h][pitch] x 16 B
     float2* flow = nullptr;                   // [B][h][pitch]
-    // tensor maps for the tile kernel's L2 prefetch (compact plans, box window): one per matrices buffer
-    bf::TileMaps maps[2];
+    // tensor maps for the tile kernel's L2 prefetch of the R blocks (compact plans, box window)
+    bf::TileMaps maps[1];
     bool have_maps = false;
 };
 
@@ -281,6 +298,9 @@ struct bf_plan {
     static constexpr int kTickets = 8;
     cudaEvent_t ev_done[kTickets] = {};         // completion events of bf_flow_series_host_async calls (ring)
     long long next_ticket = 0;
+    // OPTFLOW_USE_INITIAL_FLOW: INTER_AREA tables full resolution -> coarsest scale
+    int *ia_xofs = nullptr, *ia_xidx = nullptr, *ia_yofs = nullptr, *ia_yidx = nullptr;
+    float *ia_xwgt = nullptr, *ia_ywgt = nullptr;
     bool use_fast = true;
     bool r_half = false;        // polynomial coefficients packed in 16 B per pixel, b f32 + A f16 (fast path, uint8 input)
     int sm_count = 148;
@@ -315,8 +335,6 @@ int validate_params(const bf_params* q, int W, int H) {
     if (q->poly_n < 1) return fail(BF_E_INVALID, "poly_n must be >= 1");
     if (q->poly_n > BF_MAX_POLY_N) return fail(BF_E_UNSUPPORTED, "poly_n=%d > %d not supported", q->poly_n, BF_MAX_POLY_N);
     if (q->winsize / 2 > BF_MAX_WIN_HALF) return fail(BF_E_UNSUPPORTED, "winsize=%d too large (max %d)", q->winsize, 2 * BF_MAX_WIN_HALF + 1);
-    if (q->flags & BF_OPTFLOW_USE_INITIAL_FLOW)
-        return fail(BF_E_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is not supported (the reference path uses flags=0)");
     if (q->flags & ~(BF_OPTFLOW_FARNEBACK_GAUSSIAN | BF_OPTFLOW_USE_INITIAL_FLOW))
         return fail(BF_E_INVALID, "unknown flags 0x%x", q->flags);
     return 0;
@@ -389,7 +407,7 @@ BlurKernel choose_blur_kernel(const bf::BlurSolveArgs& a, const bf::WinCoef& wc,
 int blur_solve_ncta(const bf::BlurSolveArgs& a, const bf::WinCoef& wc, bool allow_fast, bool r_half) {
     switch (choose_blur_kernel(a, wc, allow_fast)) {
         case BK_TILE: return bf::box_fast_ncta(a.w, a.h, r_half);
-        case BK_GAUSS: return bf::gauss_fast_ncta(a.w, a.h);
+        case BK_GAUSS: return bf::gauss_fast_ncta(a.w, a.h, r_half);
         default: return cdiv(a.w, bf::kBsTW) * cdiv(a.h, bf::kBsTH);
     }
 }
@@ -517,7 +535,9 @@ struct RoiCtx {
 
 // Coarse-to-fine schedule for np pairs whose first frame is t0 (pair q = frames t0+q, t0+q+1).
 // flow_out: dense [np][H][W][2] or NULL.  roi: optional ROI reduction into roi->out rows t0+1+q.
-int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cudaStream_t st) {
+// init_flow: OPTFLOW_USE_INITIAL_FLOW -- dense [np][H][W][2] flow the coarsest scale starts from (cv2: INTER_AREA resize
+// times the scale); may alias flow_out (read at the coarsest scale, written by the last launch).
+int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cudaStream_t st, const float* init_flow = nullptr) {
     const int I = p->prm.iterations;
     const int nsc = (int)p->sc.size();
     const int slot0 = t0 % p->F;
@@ -526,6 +546,7 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
         bf::k_axes_to_f32<<<cdiv(np, 64), 64, 0, st>>>(roi->ex, roi->ey, t0 + 1, np, p->axes);
         LAUNCH_CHECK();
     }
+    if (I == 0 && init_flow) return fail(BF_E_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW with iterations = 0 is not supported");
     if (I == 0) {
         // cv2 leaves the (zero-initialised, upsampled) flow untouched: the result is identically zero
         const ScaleInfo& s = p->sc.back();
@@ -550,11 +571,19 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
     for (int i = 0; i < nsc; ++i) {
         const ScaleInfo& s = p->sc[i];
         const bool finest = (i == nsc - 1);
-        const size_t m_stride = p->r_half ? bf::m_pair_bytes<true>(s.plane) : bf::m_pair_bytes<false>(s.plane);
+        const size_t m_stride = bf::m_pair_bytes(p->r_half, s.w, s.h, s.plane);
         bf::UpdateArgs u{};
         u.R = s.R; u.plane_stride = s.plane; u.slot_stride = p->r_half ? s.plane : 5 * s.plane; u.slot0 = slot0; u.nslots = p->F;
         u.pitch = s.pitch; u.w = s.w; u.h = s.h;
-        if (i == 0) {
+        if (i == 0 && init_flow) {
+            dim3 g(cdiv(s.w, 256), s.h, np);
+            bf::k_resize_area_flow<<<g, 256, 0, st>>>((const float2*)init_flow, p->W, (size_t)p->H * p->W,
+                                                     bf::AreaTab{p->ia_xofs, p->ia_xidx, p->ia_xwgt}, bf::AreaTab{p->ia_yofs, p->ia_yidx, p->ia_ywgt},
+                                                     s.w, s.h, (float)s.scale, s.flow, s.pitch, s.plane);
+            LAUNCH_CHECK();
+            u.flow_mode = 1;
+            u.flow = s.flow; u.flow_pitch = s.pitch; u.flow_stride = s.plane;
+        } else if (i == 0) {
             u.flow_mode = 0;
         } else {
             const ScaleInfo& c = p->sc[i - 1];
@@ -588,7 +617,7 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
                 }
             }
             if ((rc = prof_begin(p, finest ? (last ? BF_PROF_ITER_LAST : BF_PROF_ITER_UPDATE) : BF_PROF_COARSE, np, st))) return rc;
-            rc = launch_blur_solve(a, p->wc, np, p->use_fast, p->r_half, st, s.have_maps ? &s.maps[it & 1] : nullptr);
+            rc = launch_blur_solve(a, p->wc, np, p->use_fast, p->r_half, st, s.have_maps ? &s.maps[0] : nullptr);
             if (rc) return rc;
             if ((rc = prof_end(p, st))) return rc;
             if (last && finest && want_roi) {
@@ -664,7 +693,8 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
         const char* rs = getenv("BTCSFLOW_R_STORAGE");
         const bool want_f32 = (flags & BF_PLAN_EXACT_F32) || (rs && strcmp(rs, "f32") == 0);
         // packed fp16 coefficients need the compile-time polyexp kernels (poly_n 5 / 7) and bounded (uint8) input
-        p->r_half = p->use_fast && !want_f32 && (params->poly_n == 5 || params->poly_n == 7);
+        // (and frames of at least 4 x 2 pixels: the packed gather reads a 2 x 2 footprint at immediate offsets)
+        p->r_half = p->use_fast && !want_f32 && (params->poly_n == 5 || params->poly_n == 7) && width >= 4 && height >= 2;
         cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     }
 
@@ -721,11 +751,21 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
         cudaMemset(s.I, 0, (size_t)p->F * s.plane * sizeof(float));
         cudaMemset(s.flow, 0, (size_t)p->B * s.plane * sizeof(float2));
     }
+    if (params->flags & BF_OPTFLOW_USE_INITIAL_FLOW) {
+        const ScaleInfo& c = p->sc.front();
+        std::vector<int> ofs, idx; std::vector<float> wgt;
+        area_table(width, c.w, ofs, idx, wgt);
+        if (upload(ofs, &p->ia_xofs) != cudaSuccess || upload(idx, &p->ia_xidx) != cudaSuccess || upload(wgt, &p->ia_xwgt) != cudaSuccess)
+            return cleanup_fail(fail(2, "table upload failed"));
+        area_table(height, c.h, ofs, idx, wgt);
+        if (upload(ofs, &p->ia_yofs) != cudaSuccess || upload(idx, &p->ia_yidx) != cudaSuccess || upload(wgt, &p->ia_ywgt) != cudaSuccess)
+            return cleanup_fail(fail(2, "table upload failed"));
+    }
     const ScaleInfo& fine = p->sc.back();
     size_t tmp_elems = 0, m_bytes = 0;
     for (auto& s : p->sc) {
         tmp_elems = std::max(tmp_elems, (size_t)p->F * height * s.pitch);
-        m_bytes = std::max(m_bytes, (size_t)p->B * (p->r_half ? bf::m_pair_bytes<true>(s.plane) : bf::m_pair_bytes<false>(s.plane)));
+        m_bytes = std::max(m_bytes, (size_t)p->B * bf::m_pair_bytes(p->r_half, s.w, s.h, s.plane));
     }
     if ((rc = plan_alloc(p, &p->tmp, tmp_elems))) return cleanup_fail(rc);
     for (int i = 0; i < 2; ++i) {
@@ -741,8 +781,7 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
             const int th = bf::box_tile_th(true);
             for (auto& s : p->sc) {
                 if (!bf::tile_fast_shape(s.w, s.h)) continue;
-                s.have_maps = bf::encode_tile_maps(&s.maps[0], p->M[0], s.R, s.w, s.h, s.pitch, s.plane, p->B, p->F, p->wc.m, th) &&
-                              bf::encode_tile_maps(&s.maps[1], p->M[1], s.R, s.w, s.h, s.pitch, s.plane, p->B, p->F, p->wc.m, th);
+                s.have_maps = bf::encode_tile_maps(&s.maps[0], s.R, s.w, s.h, s.pitch, s.plane, p->F, th);
             }
         }
     }
@@ -763,6 +802,7 @@ int bf_plan_destroy(bf_plan* p) {
         cudaFree(s.I); cudaFree(s.R); cudaFree(s.flow); cudaFree(s.tmpk);
     }
     cudaFree(p->tmp); cudaFree(p->M[0]); cudaFree(p->M[1]); cudaFree(p->axes); cudaFree(p->partial);
+    cudaFree(p->ia_xofs); cudaFree(p->ia_xidx); cudaFree(p->ia_xwgt); cudaFree(p->ia_yofs); cudaFree(p->ia_yidx); cudaFree(p->ia_ywgt);
     cudaFree(p->stage[0]); cudaFree(p->stage[1]); cudaFree(p->stage_flow);
     cudaFree(p->pair_in[0]); cudaFree(p->pair_in[1]); cudaFree(p->pair_flow);
     for (auto& hs : p->slot) {
@@ -854,7 +894,8 @@ int bf_flow_pair(bf_plan* p, const void* prev, const void* next, int dtype, size
         else rc = expand_frames<float>(p, (const float*)fr[i], pitch_bytes, 0, i, 1, st);
         if (rc) return rc;
     }
-    return run_pairs(p, 0, 1, flow_out, nullptr, st);
+    // OPTFLOW_USE_INITIAL_FLOW: flow_out is in/out, as the `flow` argument of the cv2 call
+    return run_pairs(p, 0, 1, flow_out, nullptr, st, (p->prm.flags & BF_OPTFLOW_USE_INITIAL_FLOW) ? flow_out : nullptr);
 }
 
 int bf_flow_pair_host(bf_plan* p, const void* prev, const void* next, int dtype, size_t pitch_bytes, float* flow_out,
@@ -876,6 +917,7 @@ int bf_flow_pair_host(bf_plan* p, const void* prev, const void* next, int dtype,
     }
     CU(cudaMemcpy2DAsync(p->pair_in[0], row_bytes, prev, pitch_bytes, row_bytes, p->H, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpy2DAsync(p->pair_in[1], row_bytes, next, pitch_bytes, row_bytes, p->H, cudaMemcpyHostToDevice, st));
+    if (p->prm.flags & BF_OPTFLOW_USE_INITIAL_FLOW) CU(cudaMemcpyAsync(p->pair_flow, flow_out, flow_bytes, cudaMemcpyHostToDevice, st));
     rc = bf_flow_pair(p, p->pair_in[0], p->pair_in[1], dtype, row_bytes, p->pair_flow, stream);
     if (rc) return rc;
     CU(cudaMemcpyAsync(flow_out, p->pair_flow, flow_bytes, cudaMemcpyDeviceToHost, st));
@@ -887,6 +929,7 @@ int bf_flow_series(bf_plan* p, const uint8_t* frames, int T, const double* ex, c
                    const uint8_t* roi_masks, int n_roi, float* out, float* flow_out, void* stream) {
     int rc = check_plan(p);
     if (rc) return rc;
+    if (p->prm.flags & BF_OPTFLOW_USE_INITIAL_FLOW) return fail(BF_E_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW applies to the pair call (bf_flow_pair*): a series has no caller-provided flow per pair");
     if (T < 1 || !frames) return fail(BF_E_INVALID, "need frames and T >= 1");
     if (n_roi < 0 || n_roi > p->max_rois) return fail(BF_E_INVALID, "n_roi=%d exceeds plan max_rois=%d", n_roi, p->max_rois);
     if (n_roi > 0 && (!roi_masks || !out || !ex || !ey)) return fail(BF_E_INVALID, "ROI reduction needs masks, axes and out");
@@ -920,6 +963,7 @@ int bf_flow_series_host_async(bf_plan* p, const uint8_t* frames, int T, const do
     int rc = check_plan(p);
     if (rc) return rc;
     if (!ticket) return fail(BF_E_INVALID, "ticket is NULL");
+    if (p->prm.flags & BF_OPTFLOW_USE_INITIAL_FLOW) return fail(BF_E_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW applies to the pair call (bf_flow_pair*): a series has no caller-provided flow per pair");
     if (T < 1 || !frames) return fail(BF_E_INVALID, "need frames and T >= 1");
     if (n_roi < 0 || n_roi > p->max_rois) return fail(BF_E_INVALID, "n_roi=%d exceeds plan max_rois=%d", n_roi, p->max_rois);
     if (n_roi > 0 && (!roi_masks || !out || !ex || !ey)) return fail(BF_E_INVALID, "ROI reduction needs masks, axes and out");

@@ -120,39 +120,30 @@ __device__ __forceinline__ void update_px(const float* __restrict__ R0, const fl
 }
 
 // ---- matrices M of one pair ------------------------------------------------------------------------------------------
-// Exact plans: five fp32 planes (G11, G12, G22, h1, h2), 20 B per pixel.
-// Compact plans (RH): G11, G12, G22 as fp16 planes followed by h1, h2 as fp32 planes, 14 B per pixel, with CONSISTENT
-// rounding: the structure-tensor terms G are rounded to fp16 first and h = (A b) + Gq d is then formed in fp32 from the
-// ROUNDED G.  The blurred system sum(Gq_i) d = sum(h_i) is a weighted mean of the per-pixel solutions, so perturbing the
-// weights G_i by 2^-12 moves the result only in proportion to the SPREAD of the flow inside the window, not to its
-// magnitude: measured against cv2 (NumPy emulation, tools/emulate_storage.py) this storage gives 4e-7 .. 2e-6 px mean /
-// <= 2e-4 px interior max, where all-fp16 matrices gave 1e-4 / 3e-3 (the error came from rounding h, which has to carry
-// G d to full precision).  G = A^2 terms stay far inside the fp16 range for uint8 frames (|A| <= ~48); the conversion
-// saturates (satfinite) so that an out-of-range value can never turn into inf/NaN in the window sums.
-template <bool RH> __host__ __device__ constexpr size_t m_pair_bytes(size_t plane) { return plane * (RH ? 14u : 20u); }
-
-template <bool RH> struct MView;
-template <> struct MView<false> {
-    float* p; unsigned plane;
-    __device__ __forceinline__ MView(void* base, size_t pair_stride_bytes, int pair, unsigned plane_)
-        : p(reinterpret_cast<float*>(static_cast<char*>(base) + (size_t)pair * pair_stride_bytes)), plane(plane_) {}
-    __device__ __forceinline__ float load(int c, unsigned o) const { return __ldg(p + (size_t)c * plane + o); }
-    __device__ __forceinline__ const float* gplane(int c) const { return p + (size_t)c * plane; }   // c = 0..2
-    __device__ __forceinline__ const float* hplane(int c) const { return p + (size_t)(3 + c) * plane; }   // c = 0..1
-};
-template <> struct MView<true> {
-    __half* g; float* h; unsigned plane;
-    __device__ __forceinline__ MView(void* base, size_t pair_stride_bytes, int pair, unsigned plane_) : plane(plane_) {
-        char* b = static_cast<char*>(base) + (size_t)pair * pair_stride_bytes;
-        g = reinterpret_cast<__half*>(b);
-        h = reinterpret_cast<float*>(b + (size_t)6 * plane_);
-    }
-    __device__ __forceinline__ float load(int c, unsigned o) const {
-        return c < 3 ? __half2float(__ldg(g + (size_t)c * plane + o)) : __ldg(h + (size_t)(c - 3) * plane + o);
-    }
-    __device__ __forceinline__ const __half* gplane(int c) const { return g + (size_t)c * plane; }
-    __device__ __forceinline__ const float* hplane(int c) const { return h + (size_t)c * plane; }
-};
+// Exact plans: five fp32 planes (G11, G12, G22, h1, h2), 20 B per pixel, rows of `pitch` elements.
+// Compact plans (RH): 14 B per pixel -- G11, G12, G22 as fp16 and h1, h2 as fp32 -- with CONSISTENT rounding: the
+// structure-tensor terms G are rounded to fp16 first and h = (A b) + Gq d is then formed in fp32 from the ROUNDED G.  The
+// blurred system sum(Gq_i) d = sum(h_i) is a weighted mean of the per-pixel solutions, so perturbing the weights G_i by
+// 2^-12 moves the result only in proportion to the SPREAD of the flow inside the window, not to its magnitude: measured
+// against cv2 (NumPy emulation, tools/emulate_storage.py) this storage gives 4e-7 .. 2e-6 px mean / <= 2e-4 px interior
+// max, where all-fp16 matrices gave 1e-4 / 3e-3 (the error came from rounding h, which has to carry G d to full
+// precision).  G = A^2 terms stay far inside the fp16 range for uint8 frames (|A| <= ~48); the conversion saturates
+// (satfinite) so that an out-of-range value can never turn into inf/NaN in the window sums.
+//
+// Compact matrices are stored in BLOCKS of 128 columns x 16 rows (one tile of the iteration kernel), 28 KB each:
+//     block (bx, by) at ((by * nbx) + bx) * kMbBytes;  inside it  G_c at c * 4096 + (row * 128 + col) * 2   (c = 0..2)
+//                                                                 h_c at 12288 + c * 8192 + (row * 128 + col) * 4   (c = 0..1)
+// so that, relative to one per-thread pointer, every row and channel a thread touches sits at a COMPILE-TIME offset: the
+// vertical window walk of phase 1 and the five stores of the update tail need no address arithmetic per row (the planar
+// layout cost ~5 integer instructions per load and ~20 per pixel of stores; ncu, profiles/r2b), and a tile's own block is one
+// contiguous 28 KB span (one bulk L2 prefetch).  Padding rows/columns of edge blocks are never written and stay zero.
+constexpr int kMbW = 128, kMbH = 16;
+constexpr unsigned kMbGBytes = kMbW * kMbH * 2, kMbHBytes = kMbW * kMbH * 4;          // one channel of a block
+constexpr unsigned kMbHOff = 3 * kMbGBytes;
+constexpr unsigned kMbBytes = 3 * kMbGBytes + 2 * kMbHBytes;                          // 28672
+__host__ __device__ inline size_t m_pair_bytes(bool compact, int w, int h, size_t plane) {
+    return compact ? (size_t)((w + kMbW - 1) / kMbW) * ((h + kMbH - 1) / kMbH) * kMbBytes : plane * 20u;
+}
 
 // One pixel of M on its way to memory.  Exact: five floats.  Compact: the three G terms already rounded to fp16 (raw
 // halves, two packed in g01) and the two fp32 h terms formed from those rounded values.
@@ -160,20 +151,46 @@ template <bool RH> struct MOut;
 template <> struct MOut<false> { float m[5]; };
 template <> struct MOut<true> { unsigned g01; unsigned short g2; float h1, h2; };
 
-__device__ __forceinline__ void m_store(const MView<false>& M, unsigned o, const MOut<false>& v) {
-    float* pm = M.p + o;
+template <bool RH> struct MView;
+template <> struct MView<false> {
+    float* p; unsigned plane, pitch;
+    __device__ __forceinline__ MView(void* base, size_t pair_stride_bytes, int pair, unsigned plane_, unsigned pitch_, int)
+        : p(reinterpret_cast<float*>(static_cast<char*>(base) + (size_t)pair * pair_stride_bytes)), plane(plane_), pitch(pitch_) {}
+    __device__ __forceinline__ float load(int c, int y, int x) const { return __ldg(p + (size_t)c * plane + (unsigned)y * pitch + (unsigned)x); }
+    __device__ __forceinline__ void store(int y, int x, const MOut<false>& v) const {
+        float* pm = p + (unsigned)y * pitch + (unsigned)x;
 #pragma unroll
-    for (int c = 0; c < 5; ++c) { *pm = v.m[c]; pm += M.plane; }
-}
-__device__ __forceinline__ void m_store(const MView<true>& M, unsigned o, const MOut<true>& v) {
-    unsigned short* pg = reinterpret_cast<unsigned short*>(M.g) + o;
-    pg[0] = (unsigned short)(v.g01 & 0xffffu);
-    pg[M.plane] = (unsigned short)(v.g01 >> 16);
-    pg[2u * M.plane] = v.g2;
-    float* ph = M.h + o;
-    ph[0] = v.h1;
-    ph[M.plane] = v.h2;
-}
+        for (int c = 0; c < 5; ++c) { *pm = v.m[c]; pm += plane; }
+    }
+};
+template <> struct MView<true> {
+    char* base; unsigned nbx;
+    __device__ __forceinline__ MView(void* base_, size_t pair_stride_bytes, int pair, unsigned, unsigned, int w)
+        : base(static_cast<char*>(base_) + (size_t)pair * pair_stride_bytes), nbx((unsigned)(w + kMbW - 1) / kMbW) {}
+    __device__ __forceinline__ char* block(int bx, int by) const { return base + ((size_t)((unsigned)by * nbx + (unsigned)bx)) * kMbBytes; }
+    __device__ __forceinline__ unsigned block_row_bytes() const { return nbx * kMbBytes; }      // from block (bx, by) to (bx, by + 1)
+    // byte offset of pixel (row, col) of G channel 0 / h channel 0 inside a block
+    static __device__ __forceinline__ unsigned g_off(int row, int col) { return (unsigned)(row * kMbW + col) * 2u; }
+    static __device__ __forceinline__ unsigned h_off(int row, int col) { return kMbHOff + (unsigned)(row * kMbW + col) * 4u; }
+    __device__ __forceinline__ float load(int c, int y, int x) const {
+        const char* b = block(x >> 7, y >> 4);
+        const int row = y & 15, col = x & 127;
+        if (c < 3) return __half2float(__ldg(reinterpret_cast<const __half*>(b + c * kMbGBytes + g_off(row, col))));
+        return __ldg(reinterpret_cast<const float*>(b + (c - 3) * kMbHBytes + h_off(row, col)));
+    }
+    // stores through pointers already positioned on the pixel: pg inside G channel 0, ph inside h channel 0 of the block
+    static __device__ __forceinline__ void store_at(char* pg, char* ph, const MOut<true>& v) {
+        *reinterpret_cast<unsigned short*>(pg) = (unsigned short)(v.g01 & 0xffffu);
+        *reinterpret_cast<unsigned short*>(pg + kMbGBytes) = (unsigned short)(v.g01 >> 16);
+        *reinterpret_cast<unsigned short*>(pg + 2 * kMbGBytes) = v.g2;
+        *reinterpret_cast<float*>(ph) = v.h1;
+        *reinterpret_cast<float*>(ph + kMbHBytes) = v.h2;
+    }
+    __device__ __forceinline__ void store(int y, int x, const MOut<true>& v) const {
+        char* b = block(x >> 7, y >> 4);
+        store_at(b + g_off(y & 15, x & 127), b + h_off(y & 15, x & 127), v);
+    }
+};
 
 // ---- mixed-precision helpers (sm_100a: f32 <- f16 (x f16) + f32 in one instruction, exact conversions included) --------
 __device__ __forceinline__ float fh_add(unsigned short h, float s) { float d; asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(s)); return d; }
@@ -203,33 +220,42 @@ __device__ __forceinline__ uint4 pack_r(float r0, float r1, float r2, float r3, 
 
 // UpdateMatrices from packed R, split in two so that the gather of the NEXT pixel can be in flight while this one is being
 // computed.  Branch-free: the four taps always come from a clamped footprint, and when the footprint is not strictly inside
-// (the reference's fallback branch: A from R0 alone, b1 := 0) the interpolation weights are zeroed, which yields exactly the
-// fallback values from the same arithmetic.
-struct UpdTaps { uint4 q, u00, u01, u10, u11; float fx, fy, dx, dy; bool inside; };
+// (the reference's fallback branch: A from R0 alone, b1 := 0) the interpolation weights are zeroed -- already at issue
+// time -- which yields exactly the fallback values from the same arithmetic.
+struct UpdTaps { uint4 q, u00, u01, u10, u11; float fx, gx, fy, sa, dx, dy; };
 
-__device__ __forceinline__ void update_issue_h(const uint4* __restrict__ R0, const uint4* __restrict__ R1, unsigned pitch,
+// r0px: R0 at pixel (x, y) (callers walking a column carry it as a pointer); R1: pixel (0, 0) of the next frame.
+// TINY: the image may be one pixel wide or high (runtime-parameter kernel); otherwise w, h >= 2 and the +1 taps sit at
+// immediate offsets.
+template <bool TINY = false>
+__device__ __forceinline__ void update_issue_h(const uint4* __restrict__ r0px, const uint4* __restrict__ R1, unsigned pitch,
                                                int w, int h, int x, int y, float dx, float dy, UpdTaps& t) {
-    t.q = __ldg(R0 + (unsigned)y * pitch + (unsigned)x);
-    const float fx = (float)x + dx, fy = (float)y + dy;
-    const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
-    t.fx = fx - (float)x1;
-    t.fy = fy - (float)y1;
+    t.q = __ldg(r0px);
+    const float px = (float)x + dx, py = (float)y + dy;
+    const int x1 = __float2int_rd(px), y1 = __float2int_rd(py);
+    const float fx = px - (float)x1;
+    const bool in = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+    t.fx = in ? fx : 0.f;
+    t.gx = in ? 1.f - fx : 0.f;
+    t.fy = py - (float)y1;
+    t.sa = in ? 0.5f : 1.f;
     t.dx = dx; t.dy = dy;
-    t.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-    const int cx = max(min(x1, w - 2), 0), cy = max(min(y1, h - 2), 0);          // w == 1 / h == 1: the +1 taps below clamp too
-    const int ox = (w > 1) ? 1 : 0;
-    const unsigned oy = (h > 1) ? pitch : 0u;
+    const int cx = max(min(x1, w - 2), 0), cy = max(min(y1, h - 2), 0);
     const uint4* pa = R1 + (unsigned)cy * pitch + (unsigned)cx;
-    t.u00 = __ldg(pa); t.u01 = __ldg(pa + ox); t.u10 = __ldg(pa + oy); t.u11 = __ldg(pa + oy + ox);
+    if (TINY) {
+        const int ox = (w > 1) ? 1 : 0;
+        const unsigned oy = (h > 1) ? pitch : 0u;
+        t.u00 = __ldg(pa); t.u01 = __ldg(pa + ox); t.u10 = __ldg(pa + oy); t.u11 = __ldg(pa + oy + ox);
+    } else {
+        const uint4* pb = pa + pitch;
+        t.u00 = __ldg(pa); t.u01 = __ldg(pa + 1); t.u10 = __ldg(pb); t.u11 = __ldg(pb + 1);
+    }
 }
 
 template <bool BORDER>
 __device__ __forceinline__ void update_finish_h(const UpdTaps& t, int w, int h, int x, int y, MOut<true>& o) {
-    const bool in = t.inside;
-    const float fx = in ? t.fx : 0.f, gx = in ? 1.f - t.fx : 0.f;
-    const float fy = t.fy, gy = 1.f - t.fy;
-    const float sa = in ? 0.5f : 1.f;
-    const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
+    const float gy = 1.f - t.fy;
+    const float a00 = t.gx * gy, a01 = t.fx * gy, a10 = t.gx * t.fy, a11 = t.fx * t.fy;
     // linear terms: fp32 taps, fp32 weights
     const float rb0 = a00 * __uint_as_float(t.u00.x) + a01 * __uint_as_float(t.u01.x) + a10 * __uint_as_float(t.u10.x) + a11 * __uint_as_float(t.u11.x);
     const float rb1 = a00 * __uint_as_float(t.u00.y) + a01 * __uint_as_float(t.u01.y) + a10 * __uint_as_float(t.u10.y) + a11 * __uint_as_float(t.u11.y);
@@ -246,9 +272,9 @@ __device__ __forceinline__ void update_finish_h(const UpdTaps& t, int w, int h, 
     const float axy = fh_fma(xy11, w11, fh_fma(xy10, w10, fh_fma(xy01, w01, fh_fma(xy00, w00, 0.f))));
     unsigned short qyy, qxx, qxy;
     split_h2(t.q.z, qyy, qxx); split_h2(t.q.w, qxy, z);
-    float r4 = fh_add(qyy, ayy) * sa;
-    float r5 = fh_add(qxx, axx) * sa;
-    float r6 = fh_add(qxy, axy) * (sa * 0.5f);
+    float r4 = fh_add(qyy, ayy) * t.sa;
+    float r5 = fh_add(qxx, axx) * t.sa;
+    float r6 = fh_add(qxy, axy) * (t.sa * 0.5f);
     float b2 = (__uint_as_float(t.q.x) - rb0) * 0.5f;
     float b3 = (__uint_as_float(t.q.y) - rb1) * 0.5f;
     if (BORDER && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
@@ -271,7 +297,7 @@ template <bool BORDER = true>
 __device__ __forceinline__ void update_px_h(const uint4* __restrict__ R0, const uint4* __restrict__ R1, unsigned pitch,
                                             int w, int h, int x, int y, float dx, float dy, MOut<true>& o) {
     UpdTaps t;
-    update_issue_h(R0, R1, pitch, w, h, x, y, dx, dy, t);
+    update_issue_h<true>(R0 + (unsigned)y * pitch + (unsigned)x, R1, pitch, w, h, x, y, dx, dy, t);
     update_finish_h<BORDER>(t, w, h, x, y, o);
 }
 

@@ -174,7 +174,7 @@ struct UpdateArgs {
 constexpr int kUpdRows = 4;   // 8 rows: 74 registers, slower (18.1 vs 17.3 ms per 128 pairs)
 
 template <bool RH>
-__global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
+__global__ void __launch_bounds__(256, 4) k_update(const UpdateArgs a) {
     // block = 64 columns x (4 x kUpdRows) rows; 1-D grid in decode_cta order
     const TilePos tp = decode_cta(blockIdx.x, (a.w + 63) / 64, (a.h + 4 * kUpdRows - 1) / (4 * kUpdRows), a.np, a.pair_group);
     const int x = tp.bx * 64 + threadIdx.x;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     const void* R0 = nullptr;
     const void* R1 = nullptr;
     const bool want_m = a.M != nullptr;
-    const MView<RH> Mo(a.M, a.m_stride, p, plane);
+    const MView<RH> Mo(a.M, a.m_stride, p, plane, pitch, w);
     if (want_m) {
         R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
         R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
@@ -240,17 +240,24 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         // packed coefficients: row k+1's taps are in flight while row k is computed (update_issue_h / update_finish_h)
         const uint4* R0h = static_cast<const uint4*>(R0);
         const uint4* R1h = static_cast<const uint4*>(R1);
+        // the thread's kUpdRows rows lie in one block of M (yb is a multiple of kUpdRows, which divides the block height):
+        // rows at +256 / +512 bytes from one pair of pointers
+        static_assert(kMbH % kUpdRows == 0, "a thread's rows must not straddle blocks");
+        char* blk = Mo.block(x >> 7, yb >> 4);
+        char* pg = blk + MView<true>::g_off(yb & 15, x & 127);
+        char* ph = blk + MView<true>::h_off(yb & 15, x & 127);
+        const uint4* q = R0h + (unsigned)min(yb, h - 1) * pitch + (unsigned)x;
         UpdTaps A, B;
-        update_issue_h(R0h, R1h, pitch, w, h, x, min(yb, h - 1), fl[0].x, fl[0].y, A);
+        update_issue_h(q, R1h, pitch, w, h, x, min(yb, h - 1), fl[0].x, fl[0].y, A);
 #pragma unroll
         for (int k = 0; k < kUpdRows; k += 2) {
-            update_issue_h(R0h, R1h, pitch, w, h, x, min(yb + k + 1, h - 1), fl[k + 1].x, fl[k + 1].y, B);
+            update_issue_h(R0h + (unsigned)min(yb + k + 1, h - 1) * pitch + (unsigned)x, R1h, pitch, w, h, x, min(yb + k + 1, h - 1), fl[k + 1].x, fl[k + 1].y, B);
             MOut<true> m;
             if (inner) update_finish_h<false>(A, w, h, x, yb + k, m); else update_finish_h<true>(A, w, h, x, yb + k, m);
-            if (yb + k < h) m_store(Mo, (unsigned)(yb + k) * pitch + (unsigned)x, m);
-            if (k + 2 < kUpdRows) update_issue_h(R0h, R1h, pitch, w, h, x, min(yb + k + 2, h - 1), fl[k + 2].x, fl[k + 2].y, A);
+            if (yb + k < h) MView<true>::store_at(pg + k * (kMbW * 2), ph + k * (kMbW * 4), m);
+            if (k + 2 < kUpdRows) update_issue_h(R0h + (unsigned)min(yb + k + 2, h - 1) * pitch + (unsigned)x, R1h, pitch, w, h, x, min(yb + k + 2, h - 1), fl[k + 2].x, fl[k + 2].y, A);
             if (inner) update_finish_h<false>(B, w, h, x, yb + k + 1, m); else update_finish_h<true>(B, w, h, x, yb + k + 1, m);
-            if (yb + k + 1 < h) m_store(Mo, (unsigned)(yb + k + 1) * pitch + (unsigned)x, m);
+            if (yb + k + 1 < h) MView<true>::store_at(pg + (k + 1) * (kMbW * 2), ph + (k + 1) * (kMbW * 4), m);
         }
     } else {
 #pragma unroll
@@ -260,7 +267,7 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
             MOut<false> m;
             if (inner) update_px_any<false, false>(R0, R1, plane, pitch, w, h, x, y, fl[k].x, fl[k].y, m);
             else update_px_any<false, true>(R0, R1, plane, pitch, w, h, x, y, fl[k].x, fl[k].y, m);
-            m_store(Mo, (unsigned)y * pitch + (unsigned)x, m);
+            Mo.store(y, x, m);
         }
     }
 }
@@ -278,13 +285,13 @@ __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs 
     const int m = wc.m;
     const int x0 = blockIdx.x * kBsTW, y0 = blockIdx.y * kBsTH;
     const int p = blockIdx.z;
-    const MView<RH> Mp(const_cast<void*>(a.M), a.m_stride, p, (unsigned)a.plane_stride);
+    const MView<RH> Mp(const_cast<void*>(a.M), a.m_stride, p, (unsigned)a.plane_stride, (unsigned)a.pitch, a.w);
     const int tw = kBsTW + 2 * m;
     const int w = a.w, h = a.h;
     for (int it = threadIdx.x; it < 5 * tw; it += blockDim.x) {
         const int c = it / tw, tx = it - c * tw;
         const int gx = min(max(x0 - m + tx, 0), w - 1);
-        auto at = [&](int row) { return Mp.load(c, (unsigned)row * (unsigned)a.pitch + (unsigned)gx); };
+        auto at = [&](int row) { return Mp.load(c, row, gx); };
         if (wc.gauss) {
             for (int ty = 0; ty < kBsTH; ++ty) {
                 const int gy = min(y0 + ty, h - 1);
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(256) k_blur_solve_generic(const BlurSolveArgs 
             const void* R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
             MOut<RH> mm;
             update_px_any<RH, true>(R0, R1, (unsigned)a.plane_stride, (unsigned)a.pitch, w, h, x, y, fl.x, fl.y, mm);
-            m_store(MView<RH>(a.Mout, a.m_stride, p, (unsigned)a.plane_stride), (unsigned)y * (unsigned)a.pitch + (unsigned)x, mm);
+            MView<RH>(a.Mout, a.m_stride, p, (unsigned)a.plane_stride, (unsigned)a.pitch, w).store(y, x, mm);
         }
     }
     if (a.partial) roi_reduce_store(a, p, x, y, valid, fl, s_red);
@@ -376,6 +383,28 @@ __global__ void k_roi_finalize(const float* __restrict__ partial, int n_pairs, i
     const float nanv = __int_as_float(0x7fc00000);
 #pragma unroll
     for (int k = 0; k < 3; ++k) o[k] = (ok && s[3 + k] > 0.0) ? (float)(s[k] / s[3 + k]) : nanv;
+}
+
+// OPTFLOW_USE_INITIAL_FLOW: the caller's full-resolution flow resized to the coarsest scale with cv2's INTER_AREA weights
+// (tables built on the host: for destination index d the source taps ofs[d] .. ofs[d+1]-1) and multiplied by the scale.
+struct AreaTab { const int* ofs; const int* idx; const float* wgt; };
+__global__ void __launch_bounds__(256) k_resize_area_flow(const float2* __restrict__ src, int W, size_t src_stride, AreaTab tx, AreaTab ty,
+                                                          int w, int h, float mult, float2* __restrict__ dst, int dst_pitch, size_t dst_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, p = blockIdx.z;
+    if (x >= w || y >= h) return;
+    const float2* s = src + (size_t)p * src_stride;
+    float ax = 0.f, ay = 0.f;
+    for (int j = ty.ofs[y]; j < ty.ofs[y + 1]; ++j) {
+        const float2* row = s + (size_t)ty.idx[j] * W;
+        float rx = 0.f, ry = 0.f;
+        for (int i = tx.ofs[x]; i < tx.ofs[x + 1]; ++i) {
+            const float2 v = row[tx.idx[i]];
+            const float a = tx.wgt[i];
+            rx += v.x * a; ry += v.y * a;
+        }
+        ax += rx * ty.wgt[j]; ay += ry * ty.wgt[j];
+    }
+    dst[(size_t)p * dst_stride + (size_t)y * dst_pitch + x] = make_float2(ax * mult, ay * mult);
 }
 
 // axes[p] = (float)ex[t], ... for pairs t = t_first + p (python float -> float32 as numpy does, optical_flow.py:180-181)

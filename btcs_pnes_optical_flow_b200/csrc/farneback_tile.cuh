@@ -35,7 +35,10 @@ struct FastBoxCfg {
     static constexpr int VP = kFbTW + 2 * HALO + 4;            // shared row pitch (floats, multiple of 4)
     static constexpr int WIN = 2 * MH + 1;
     static constexpr int NCH = (D + 2 * MH + 3) / 4 + 1;       // float4 chunks a 4-output group reads
-    static constexpr int V_FLOATS = 5 * TH * VP;
+    // compact tiles store the vertical sums as prefix sums inside each 4-column group, one plane per component (prefix_store):
+    // row = 4 planes x NC4 groups
+    static constexpr int VROW = RH ? 4 * NC4 : VP;             // floats per (channel, row)
+    static constexpr int V_FLOATS = 5 * TH * VROW;
     static constexpr int NTASK = RH ? 3 * NC4 + 2 * NC2 : 5 * NC4;   // phase-1 column tasks per tile
     static constexpr int PF = TH >= 32 ? 8 : 4;                // register prefetch depth in phase 1
     // CTAs per SM: what registers (window = WIN rows x 2 registers compact, x 4 exact) and shared memory allow
@@ -80,11 +83,10 @@ __device__ __forceinline__ void prefetch_l2_box(const CUtensorMap* tm, int c0, i
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
                  ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-// Tensor maps of one launch of the tile kernels (built per scale at plan creation, bf::encode_tile_maps):
-// g / hh = input matrices, fp16 G planes {x, y, 3, pair} and fp32 h planes {x, y, 2, pair}, boxes (TW + 2 HALO) x
-// (TH + 2 MH) x channels x 1; r0 / r1 = packed R ring {128 words = 32 pixels, x / 32, y, slot}, boxes 128 x 4 x TH x 1
-// and 128 x 6 x (TH + 4) x 1.
-struct TileMaps { CUtensorMap g, hh, r0, r1; };
+// Tensor maps of one launch of the box tile kernel (built per scale at plan creation, bf::encode_tile_maps): r0 / r1 = packed
+// R ring {128 words = 32 pixels, x / 32, y, slot}, boxes 128 x 4 x TH x 1 and 128 x 6 x (TH + 4) x 1.  (The matrices need
+// no map: their blocks are contiguous spans.)
+struct TileMaps { CUtensorMap r0, r1; };
 
 // ---- one row of a column group as it sits in the phase-1 register window ----------------------------------------------
 // RowH4: four fp16 columns kept packed (uint2), consumed by the mixed-precision add of sm_100a (FHADD: f32 + f16 -> f32,
@@ -155,18 +157,43 @@ __device__ __forceinline__ void sum_store(float* dst, const float2& s, int mode,
     }
 }
 
+// Compact tiles keep the vertical sums of a row as PREFIX sums inside each 4-column group, one plane of `ng` groups per
+// component, Vp[channel][row][k][group]:
+//     G planes (one 4-column task per group)   k = 0..3:  c0, c0+c1, c0+c1+c2, c0+c1+c2+c3
+//     h planes (two 2-column tasks per group)  k = 0..3:  c0, c0+c1, c2, c2+c3
+// The horizontal pass then needs, per channel and 4 outputs, the components of the two groups its windows start and end in
+// and ONE value (the group sum) of every group in between, all read with lanes on consecutive groups (conflict-free
+// LDS.32): 10 shared-memory wavefronts per warp instead of the 20 of five LDS.128 on raw sums, and 11 additions per 4
+// outputs instead of 23.  (The kernel is bound by LSU wavefronts: 81 % of peak, ncu profiles/r2c.)
+template <bool EDGE>
+__device__ __forceinline__ void prefix_store(float* dst, const float4& s0, int mode, int kl, int ng) {
+    float4 s = s0;
+    if (EDGE && mode != 0) {
+        const float e = (mode == 1 || kl == 0) ? s.x : (kl == 1 ? s.y : (kl == 2 ? s.z : s.w));
+        const bool keep = mode == 3;
+        s = make_float4(keep ? s.x : e, (keep && kl >= 1) ? s.y : e, (keep && kl >= 2) ? s.z : e, e);
+    }
+    const float p2 = s.x + s.y, p3 = p2 + s.z;
+    dst[0] = s.x; dst[ng] = p2; dst[2 * ng] = p3; dst[3 * ng] = p3 + s.w;
+}
+template <bool EDGE>
+__device__ __forceinline__ void prefix_store(float* dst, const float2& s0, int mode, int kl, int ng) {
+    float2 s = s0;
+    if (EDGE && mode != 0) {
+        const float e = (mode == 1 || kl == 0) ? s.x : s.y;
+        s = make_float2(mode == 3 ? s.x : e, e);
+    }
+    dst[0] = s.x; dst[ng] = s.x + s.y;
+}
+
 // Vertical (2MH+1)-row box sums of one column group for TH consecutive output rows; register ring window, software
-// prefetch PF rows ahead.  ROWS_IN: the tile's rows (with halo) lie inside the image, `src` already points at the first
-// halo row.  Otherwise rows are clamped to [0, h-1] (replicate) starting from row `yb`.
-template <int MH, bool ROWS_IN, bool EDGE, int TH, int PF, typename Row>
-__device__ __forceinline__ void vertical_box_sums(const typename Row::Elem* __restrict__ src, unsigned pitch, int yb, int h,
-                                                  int mode, int kl, float* __restrict__ dst, int vp) {
+// prefetch PF rows ahead.  ld(i) returns row i of the tile's TH + 2MH input rows (i ascends strictly from call to call and
+// is a compile-time constant after unrolling).
+// PREFIX: store in the prefix-plane layout (prefix_store; `ng` groups per plane) instead of raw sums.
+template <int MH, bool EDGE, int TH, int PF, typename Row, bool PREFIX = false, typename LoadFn>
+__device__ __forceinline__ void vertical_box_sums(LoadFn ld, int mode, int kl, float* __restrict__ dst, int vp, int ng = 0) {
     constexpr int WIN = 2 * MH + 1, NROW = TH + 2 * MH;
-    auto ld = [&](int i) -> Row {
-        if (ROWS_IN) return Row::load(src + (unsigned)i * pitch);
-        const int r = min(max(yb + i, 0), h - 1);
-        return Row::load(src + (unsigned)r * pitch);
-    };
+    static_assert(PF <= TH - 1, "prefetch depth exceeds the rows that follow the first window");
     Row win[WIN];
 #pragma unroll
     for (int i = 0; i < WIN; ++i) win[i] = ld(i);
@@ -176,7 +203,7 @@ __device__ __forceinline__ void vertical_box_sums(const typename Row::Elem* __re
     sum_store<EDGE>(dst, s, mode, kl);
     Row pre[PF];
 #pragma unroll
-    for (int i = 0; i < PF; ++i) pre[i] = ld(min(WIN + i, NROW - 1));
+    for (int i = 0; i < PF; ++i) pre[i] = ld(WIN + i);
 #pragma unroll
     for (int j = 1; j < TH; ++j) {
         const Row nv = pre[(j - 1) % PF];
@@ -184,23 +211,65 @@ __device__ __forceinline__ void vertical_box_sums(const typename Row::Elem* __re
         const Row ov = win[(j - 1) % WIN];
         Row::slide(s, nv, ov);
         win[(j - 1) % WIN] = nv;
-        sum_store<EDGE>(dst + j * vp, s, mode, kl);
+        if (PREFIX) prefix_store<EDGE>(dst + j * vp, s, mode, kl, ng); else sum_store<EDGE>(dst + j * vp, s, mode, kl);
     }
 }
 
-// One phase-1 task: the column group that starts at image column gx (aligned to the image origin, possibly outside).
+// Which column group a phase-1 task reads: groups are aligned to the image origin, so a group is entirely inside the image
+// (mode 0), left of it (1), right of it (2), or the one group that straddles the right edge (3).
+template <int GW>
+__device__ __forceinline__ void column_mode(int gx, int w, int& mode, int& kl, int& cgx) {
+    const int wl = (w - 1) & ~(GW - 1);                               // last group that holds a pixel
+    kl = (w - 1) & (GW - 1);                                          // ... and that pixel's lane
+    mode = gx < 0 ? 1 : (gx > wl ? 2 : ((gx == wl && kl != GW - 1) ? 3 : 0));
+    cgx = mode == 1 ? 0 : (mode == 2 ? wl : gx);
+}
+
+// One phase-1 task on planar fp32 matrices (exact plans): rows `pitch` elements apart; interior tiles step one pointer.
 template <int MH, int TH, int PF, typename Row>
-__device__ __forceinline__ void column_task(const typename Row::Elem* __restrict__ plane_base, unsigned pitch, int w, int h, int gx,
-                                            int y0, bool rows_in, float* __restrict__ dst, int vp) {
-    constexpr int GW = Row::GW;
-    const int wl = (w - 1) & ~(GW - 1), kl = (w - 1) & (GW - 1);      // last group that holds a pixel, and that pixel's lane
-    const int mode = gx < 0 ? 1 : (gx > wl ? 2 : ((gx == wl && kl != GW - 1) ? 3 : 0));
-    const int cgx = mode == 1 ? 0 : (mode == 2 ? wl : gx);
-    const typename Row::Elem* src = plane_base + (unsigned)cgx;
-    // rows inside / clamped x interior column / replicated edge column (edge columns are rare and were costing 7.5 FSEL per
-    // pixel when handled by selects)
-    if (mode == 0 && rows_in) vertical_box_sums<MH, true, false, TH, PF, Row>(src + (unsigned)(y0 - MH) * pitch, pitch, 0, 0, 0, 0, dst, vp);
-    else vertical_box_sums<MH, false, true, TH, PF, Row>(src, pitch, y0 - MH, h, mode, kl, dst, vp);
+__device__ __forceinline__ void column_task_planar(const float* __restrict__ plane_base, unsigned pitch, int w, int h, int gx,
+                                                   int y0, bool rows_in, float* __restrict__ dst, int vp) {
+    int mode, kl, cgx;
+    column_mode<Row::GW>(gx, w, mode, kl, cgx);
+    const float* src = plane_base + (unsigned)cgx;
+    if (mode == 0 && rows_in) {
+        const float* pl = src + (unsigned)(y0 - MH) * pitch;
+        vertical_box_sums<MH, false, TH, PF, Row>([&](int) { const Row r = Row::load(pl); pl += pitch; return r; }, 0, 0, dst, vp);
+    } else {
+        vertical_box_sums<MH, true, TH, PF, Row>([&](int i) { return Row::load(src + (unsigned)min(max(y0 - MH + i, 0), h - 1) * pitch); },
+                                                 mode, kl, dst, vp);
+    }
+}
+
+// One phase-1 task on blocked matrices (compact plans; the tile IS block (bx, by), TH == kMbH): `choff` = byte offset of the
+// channel inside a block, ES = element size.  Interior tiles read every row at a compile-time offset from three pointers
+// (the blocks above, of, and below the tile); tiles at the image border clamp the row (replicate) and locate its block.
+template <int MH, int PF, typename Row, int ES>
+__device__ __forceinline__ void column_task_blocked(const MView<true>& Mv, unsigned choff, int w, int h, int gx, int y0,
+                                                    bool rows_in, float* __restrict__ dst, int vp, int ng) {
+    static_assert(MH <= kMbH, "the window must not reach past the neighbouring blocks");
+    int mode, kl, cgx;
+    column_mode<Row::GW>(gx, w, mode, kl, cgx);
+    const unsigned coff = choff + (unsigned)(cgx & (kMbW - 1)) * ES;
+    constexpr int RB = kMbW * ES;                                     // bytes per block row
+    using Elem = typename Row::Elem;
+    if (mode == 0 && rows_in) {
+        const char* pc = Mv.block(cgx >> 7, y0 >> 4) + coff;
+        const char* pa = pc - Mv.block_row_bytes();
+        const char* pb = pc + Mv.block_row_bytes();
+        vertical_box_sums<MH, false, kMbH, PF, Row, true>([&](int i) {
+            const int r = i - MH;                                     // row relative to the tile (compile-time after unrolling)
+            const char* q = r < 0 ? pa + (kMbH + r) * RB : (r < kMbH ? pc + r * RB : pb + (r - kMbH) * RB);
+            return Row::load(reinterpret_cast<const Elem*>(q));
+        }, 0, 0, dst, vp, ng);
+    } else {
+        const char* pcol = Mv.block(cgx >> 7, 0) + coff;
+        const unsigned brow = Mv.block_row_bytes();
+        vertical_box_sums<MH, true, kMbH, PF, Row, true>([&](int i) {
+            const int r = min(max(y0 - MH + i, 0), h - 1);
+            return Row::load(reinterpret_cast<const Elem*>(pcol + (size_t)(r >> 4) * brow + (unsigned)(r & 15) * RB));
+        }, mode, kl, dst, vp, ng);
+    }
 }
 
 // Lines of R that a block of rows [ya, ya+NROWS) x columns [x0, x0+128) will touch in its update tail: R0 under the
@@ -242,53 +311,72 @@ __device__ __forceinline__ void prefetch_r_block(const void* R0v, const void* R1
     }
 }
 
-// M tile (with halo) into L2, per 128-byte line (launches without tensor maps).
-template <bool RH, int MH, int HALO, int TH>
-__device__ __forceinline__ void prefetch_m_tile(const MView<RH>& Mv, unsigned pitch, int w, int h, int x0, int y0, int tid, int nthreads) {
+// One instruction requests a whole contiguous span into L2 through the bulk-copy unit.  p 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void prefetch_l2_span(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// M tile (with halo) into L2.  Blocked matrices: the tile's own block and the blocks above / below are contiguous 28 KB
+// spans (three instructions; the rows of the neighbours this tile does not read are read by their own tiles a few CTAs
+// earlier / later, so nothing extra travels from HBM).  Planar matrices: per 128-byte line.
+template <int MH, int HALO, int TH>
+__device__ __forceinline__ void prefetch_m_tile(const MView<true>& Mv, int w, int h, int x0, int y0, int tid, int) {
+    if (tid == 0) {
+        const int bx = x0 >> 7, by = y0 >> 4, nby = (h + kMbH - 1) / kMbH;
+        prefetch_l2_span(Mv.block(bx, by), kMbBytes);
+        if (by > 0) prefetch_l2_span(Mv.block(bx, by - 1), kMbBytes);
+        if (by + 1 < nby) prefetch_l2_span(Mv.block(bx, by + 1), kMbBytes);
+    }
+}
+template <int MH, int HALO, int TH>
+__device__ __forceinline__ void prefetch_m_tile(const MView<false>& Mv, int w, int h, int x0, int y0, int tid, int nthreads) {
     constexpr int NROW = TH + 2 * MH;
-    constexpr int NL = (kFbTW + 2 * HALO) / 32 + 2;                     // 128-byte lines of fp32 per tile row (incl. misalignment)
+    constexpr int NL = (kFbTW + 2 * HALO) / 32 + 2;                     // 128-byte lines per tile row (incl. misalignment)
     const int xlo = max(x0 - HALO, 0) & ~31, xmaxl = max((w - 1) & ~31, 0);
     for (int e = tid; e < NROW * NL; e += nthreads) {
         const int r = e / NL, l = e - r * NL;
         const int yy = min(max(y0 - MH + r, 0), h - 1), xx = min(xlo + l * 32, xmaxl);
-        const unsigned o = (unsigned)yy * pitch + (unsigned)xx;
+        const float* q = Mv.p + (unsigned)yy * Mv.pitch + (unsigned)xx;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) prefetch_l2(Mv.hplane(c) + o);
-        if (!RH || (l & 1) == 0) {                                       // fp16 planes: a line holds 64 columns
-#pragma unroll
-            for (int c = 0; c < 3; ++c) prefetch_l2(Mv.gplane(c) + o);
-        }
+        for (int c = 0; c < 5; ++c) prefetch_l2(q + (size_t)c * Mv.plane);
     }
 }
 
-// Update tail of one warp: N pixels per lane, lane = column within a 32-wide group, pixel i+1's taps in flight while
-// pixel i is computed.  EDGE: the tile may stick out of the image or touch the 5-px attenuation ring.
-template <bool EDGE, int N, typename RowFn, typename ColFn>
+// Update tail of one warp on a compact plan: N pixels per lane walking DOWN one column (lane = column within a 32-wide
+// group), pixel i+1's taps in flight while pixel i is computed.  A rolled loop over pixel pairs (the fully unrolled form was
+// 16 KB of straight-line code per variant: a third of the tail's stall samples were instruction-cache misses; ncu,
+// profiles/r2b) with every address carried as a pointer: R0 down the column, the M' block rows at +256 / +512 bytes.
+// EDGE: the tile may stick out of the image or touch the 5-px attenuation ring.
+template <bool EDGE, int N>
 __device__ __forceinline__ void update_tail_pipelined(const uint4* __restrict__ R0, const uint4* __restrict__ R1,
-                                                      const float2* __restrict__ F, const MView<true>& Mo,
-                                                      unsigned pitch, int w, int h, int x0, int y0, RowFn tail_row, ColFn tail_col) {
-    auto issue = [&](int i, UpdTaps& t) {
-        const int r = tail_row(i), cx = tail_col(i);
-        const float2 f = F[r * kFbTW + cx];
-        int x = x0 + cx, y = y0 + r;
-        if (EDGE) { x = min(x, w - 1); y = min(y, h - 1); }
-        update_issue_h(R0, R1, pitch, w, h, x, y, f.x, f.y, t);
-    };
-    auto finish = [&](int i, const UpdTaps& t) {
-        const int r = tail_row(i), cx = tail_col(i);
-        const int x = x0 + cx, y = y0 + r;
-        MOut<true> mm;
-        update_finish_h<EDGE>(t, w, h, x, y, mm);
-        if (!EDGE || (x < w && y < h)) m_store(Mo, (unsigned)y * pitch + (unsigned)x, mm);
+                                                      const float2* __restrict__ F, const MView<true>& Mo, unsigned pitch,
+                                                      int w, int h, int x0, int y0, int r0, int cx) {
+    static_assert(N % 2 == 0, "pixels are processed in pairs");
+    const int x = x0 + cx, xc = EDGE ? min(x, w - 1) : x;
+    const float2* fp = F + r0 * kFbTW + cx;
+    const uint4* q0 = R0 + (unsigned)(EDGE ? min(y0 + r0, h - 1) : y0 + r0) * pitch + (unsigned)xc;
+    char* blk = Mo.block(x0 >> 7, y0 >> 4);
+    char* pg = blk + MView<true>::g_off(r0, cx);
+    char* ph = blk + MView<true>::h_off(r0, cx);
+    int y = y0 + r0;
+    auto issue = [&](UpdTaps& t, int yy, const float2* f, const uint4* q) {
+        const float2 fl = *f;
+        update_issue_h(q, R1, pitch, w, h, xc, EDGE ? min(yy, h - 1) : yy, fl.x, fl.y, t);
     };
     UpdTaps A, B;
-    issue(0, A);
-#pragma unroll
+    issue(A, y, fp, q0);
+#pragma unroll 1
     for (int i = 0; i < N; i += 2) {
-        issue(i + 1, B);
-        finish(i, A);
-        if (i + 2 < N) issue(i + 2, A);
-        finish(i + 1, B);
+        const uint4* q1 = (!EDGE || y + 1 < h) ? q0 + pitch : q0;
+        issue(B, y + 1, fp + kFbTW, q1);
+        MOut<true> mm;
+        update_finish_h<EDGE>(A, w, h, x, y, mm);
+        if (!EDGE || (x < w && y < h)) MView<true>::store_at(pg, ph, mm);
+        const uint4* q2 = (!EDGE || y + 2 < h) ? q1 + pitch : q1;
+        if (i + 2 < N) issue(A, y + 2, fp + 2 * kFbTW, q2);
+        update_finish_h<EDGE>(B, w, h, x, y + 1, mm);
+        if (!EDGE || (x < w && y + 1 < h)) MView<true>::store_at(pg + kMbW * 2, ph + kMbW * 4, mm);
+        fp += 2 * kFbTW; q0 = q2; pg += 2 * kMbW * 2; ph += 2 * kMbW * 4; y += 2;
     }
 }
 
@@ -304,26 +392,25 @@ __device__ __forceinline__ void tile_tail(const BlurSolveArgs& a, const float2* 
     const int w = a.w, h = a.h;
     const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
     const int tail_r0 = (wid >> 2) * N, tail_c0 = (wid & 3) * 32 + lane;
-    auto tail_row = [&](int i) { return tail_r0 + i; };
-    auto tail_col = [&](int) { return tail_c0; };
     if (a.flow || a.Mout) {
         float2* fo = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
         const bool want_m = a.Mout != nullptr;
-        const MView<RH> Mo(a.Mout, a.m_stride, p, plane);
+        const MView<RH> Mo(a.Mout, a.m_stride, p, plane, pitch, w);
         // interior tiles (85 % at 1080p): bounds and the 5-px attenuation ring are decided once per tile
         const bool inner = (x0 >= 5) && (y0 >= 5) && (x0 + kFbTW <= w - 5) && (y0 + TH <= h - 5);
         bool done = false;
         if constexpr (RH) {
+            static_assert(TH == kMbH, "compact tiles are the 16-row blocks of the matrices");
             if (want_m && !fo) {
-                if (inner) update_tail_pipelined<false, N>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, pitch, w, h, x0, y0, tail_row, tail_col);
-                else update_tail_pipelined<true, N>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, pitch, w, h, x0, y0, tail_row, tail_col);
+                if (inner) update_tail_pipelined<false, N>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, pitch, w, h, x0, y0, tail_r0, tail_c0);
+                else update_tail_pipelined<true, N>(static_cast<const uint4*>(R0), static_cast<const uint4*>(R1), F, Mo, pitch, w, h, x0, y0, tail_r0, tail_c0);
                 done = true;
             }
         }
         if (!done) {
-#pragma unroll 4
+#pragma unroll 2
             for (int i = 0; i < N; ++i) {
-                const int r = tail_row(i), cx = tail_col(i);
+                const int r = tail_r0 + i, cx = tail_c0;
                 const int x = x0 + cx, y = y0 + r;
                 if (x < w && y < h) {
                     const float2 f = F[r * kFbTW + cx];
@@ -332,7 +419,7 @@ __device__ __forceinline__ void tile_tail(const BlurSolveArgs& a, const float2* 
                         MOut<RH> mm;
                         if (inner) update_px_any<RH, false>(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
                         else update_px_any<RH, true>(R0, R1, plane, pitch, w, h, x, y, f.x, f.y, mm);
-                        m_store(Mo, (unsigned)y * pitch + (unsigned)x, mm);
+                        Mo.store(y, x, mm);
                     }
                 }
             }
@@ -341,20 +428,66 @@ __device__ __forceinline__ void tile_tail(const BlurSolveArgs& a, const float2* 
     if (a.partial) {
         const float* ax = a.axes + p * 4;
         const float e00 = ax[0], e01 = ax[1], e10 = ax[2], e11 = ax[3];
+        const int x = x0 + tail_c0;
         for (int roi = 0; roi < a.n_roi; ++roi) {
-            const uint8_t* mk = a.masks + (size_t)roi * a.mask_stride;
+            const uint8_t* mk = a.masks + (size_t)roi * a.mask_stride + (size_t)(y0 + tail_r0) * a.mask_pitch + x;
             RoiAcc acc;
 #pragma unroll 4
             for (int i = 0; i < N; ++i) {
-                const int r = tail_row(i), cx = tail_col(i);
-                const int x = x0 + cx, y = y0 + r;
-                if (x < w && y < h && mk[(size_t)y * a.mask_pitch + x] != 0) {
-                    const float2 f = F[r * kFbTW + cx];
+                if (x < w && y0 + tail_r0 + i < h && mk[(size_t)i * a.mask_pitch] != 0) {
+                    const float2 f = F[(tail_r0 + i) * kFbTW + tail_c0];
                     acc.add(f.x * e00 + f.y * e01, f.x * e10 + f.y * e11);
                 }
             }
             roi_cta_store(acc, s_red, a.partial + (((size_t)p * a.n_roi + roi) * ncta + cta) * kRoiVals);
         }
+    }
+}
+
+// Horizontal (2MH+1)-column box sums of 4 adjacent outputs from the prefix planes of one (channel, row).  `base` points at
+// plane 0 of the group that holds halo column 4l (l = the thread's output group): the window of output j covers halo columns
+// 4l + D + j .. 4l + D + j + 2MH.  Each window is normalised to: optional head (a suffix of group a), full groups a+1 .. b-1,
+// optional tail (a prefix of group b); the full groups common to the four windows are summed once.
+template <int MH, int D>
+struct HWin {
+    static __host__ __device__ constexpr int os(int j) { return (D + j) & 3; }
+    static __host__ __device__ constexpr int oe(int j) { return (D + j + 2 * MH) & 3; }
+    static __host__ __device__ constexpr int a(int j) { return ((D + j) >> 2) - (os(j) == 0 ? 1 : 0); }             // start on a group boundary: no head
+    static __host__ __device__ constexpr int b(int j) { return ((D + j + 2 * MH) >> 2) + (oe(j) == 3 ? 1 : 0); }    // end on a group boundary: no tail
+    static __host__ __device__ constexpr int cmax(int x, int y) { return x > y ? x : y; }
+    static __host__ __device__ constexpr int cmin(int x, int y) { return x < y ? x : y; }
+    static constexpr int AMIN = cmin(cmin(a(0), a(1)), cmin(a(2), a(3))), AMAX = cmax(cmax(a(0), a(1)), cmax(a(2), a(3)));
+    static constexpr int BMIN = cmin(cmin(b(0), b(1)), cmin(b(2), b(3))), BMAX = cmax(cmax(b(0), b(1)), cmax(b(2), b(3)));
+};
+
+// HPAIR: h planes (components c0, c0+c1, c2, c2+c3).  Every index below is a compile-time constant after unrolling.
+template <int MH, int D, bool HPAIR>
+__device__ __forceinline__ void hwindow4(const float* __restrict__ base, int ng, float out[4]) {
+    using W = HWin<MH, D>;
+    auto comp = [&](int k, int g) { return base[k * ng + g]; };
+    auto gsum = [&](int g) { return HPAIR ? comp(1, g) + comp(3, g) : comp(3, g); };                          // c0 + .. + c3
+    auto pref = [&](int g, int k) {                                                                           // c0 + .. + ck, k = 0..2
+        return HPAIR ? (k == 2 ? comp(1, g) + comp(2, g) : comp(k, g)) : comp(k, g);
+    };
+    float gs[W::BMAX - W::AMIN + 1];                              // group sums of every group a window may fully cover
+#pragma unroll
+    for (int g = W::AMIN + 1; g < W::BMAX; ++g) gs[g - W::AMIN] = gsum(g);
+    float mid = 0.f;                                              // groups that are full for all four outputs
+#pragma unroll
+    for (int g = W::AMAX + 1; g < W::BMIN; ++g) mid = (g == W::AMAX + 1) ? gs[g - W::AMIN] : mid + gs[g - W::AMIN];
+    constexpr bool have_mid = W::AMAX + 1 < W::BMIN;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float t = mid;
+        bool have = have_mid;
+#pragma unroll
+        for (int g = W::AMIN + 1; g < W::BMAX; ++g) {
+            const bool common = g > W::AMAX && g < W::BMIN;
+            if (!common && g > W::a(j) && g < W::b(j)) { t = have ? t + gs[g - W::AMIN] : gs[g - W::AMIN]; have = true; }
+        }
+        if (W::os(j) != 0) { const float hd = gsum(W::a(j)) - pref(W::a(j), W::os(j) - 1); t = have ? t + hd : hd; have = true; }
+        if (W::oe(j) != 3) { const float tl = pref(W::b(j), W::oe(j)); t = have ? t + tl : tl; have = true; }
+        out[j] = t;
     }
 }
 
@@ -375,9 +508,10 @@ __device__ __forceinline__ void solve4(const float gs[5][4], float reg, float2 f
     }
 }
 
-template <int MH, bool RH, int TH>
-__global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg, const bool use_maps,
-                                                                                    const __grid_constant__ TileMaps maps) {
+// CT: CTAs per SM the register allocation is capped for (0 = what the window size allows, FastBoxCfg::CTAS).
+template <int MH, bool RH, int TH, int CT = 0>
+__global__ void __launch_bounds__(256, CT ? CT : FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg, const bool use_maps,
+                                                                                              const __grid_constant__ TileMaps maps) {
     using C = FastBoxCfg<MH, TH, RH>;
     constexpr int NT = 256, NW = 8, RG = TH / NW;
     extern __shared__ __align__(16) float smem[];
@@ -390,7 +524,7 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solv
     const TilePos tp = decode_cta(blockIdx.x, nbx, nby, a.np, a.pair_group);
     const int x0 = tp.bx * kFbTW, y0 = tp.by * TH, p = tp.p;
     const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
-    const MView<RH> Mv(const_cast<void*>(a.M), a.m_stride, p, plane);
+    const MView<RH> Mv(const_cast<void*>(a.M), a.m_stride, p, plane, pitch, w);
     BF_TRACE_STAMP(0);
 
     // A lone CTA of this kernel takes ~22 us (ncu, profiles/): its time is a chain of HBM round trips, not bandwidth.
@@ -403,41 +537,37 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solv
         R0 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p, a.nslots));
         R1 = r_slot_ptr<RH>(a.R, a.slot_stride, ring_slot(a.slot0, p + 1, a.nslots));
     }
-    if (RH && use_maps) {
-        if (tid == 0) {
-            prefetch_l2_box(&maps.g, x0 - C::HALO, y0 - MH, 0, p);
-            prefetch_l2_box(&maps.hh, x0 - C::HALO, y0 - MH, 0, p);
-            if (a.Mout) {
+    prefetch_m_tile<MH, C::HALO, TH>(Mv, w, h, x0, y0, tid, NT);
+    if (a.Mout) {
+        if (RH && use_maps) {
+            if (tid == 32) {                                            // another warp than the M prefetches
                 prefetch_l2_box(&maps.r0, 0, x0 / 32, y0, ring_slot(a.slot0, p, a.nslots));
                 prefetch_l2_box(&maps.r1, 0, x0 / 32 - 1, y0 - 2, ring_slot(a.slot0, p + 1, a.nslots));
             }
+        } else {
+            prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, NT);
         }
-    } else {
-        prefetch_m_tile<RH, MH, C::HALO, TH>(Mv, pitch, w, h, x0, y0, tid, NT);
-        if (a.Mout) prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, NT);
     }
 
     BF_TRACE_STAMP(1);
     // ---------------- phase 1: vertical sums ----------------
-    // Column groups are aligned to the image origin: a group is entirely inside the image, entirely left of it, entirely
-    // right of it, or the one group that straddles the right edge (column_task).
     const bool rows_in = (y0 - MH >= 0) && (y0 + TH + MH <= h);      // block-uniform: no row clamping needed
     for (int task = tid; task < C::NTASK; task += NT) {
         if constexpr (RH) {
             if (task < 3 * C::NC4) {
                 const int c = task / C::NC4, q = task - c * C::NC4;
-                column_task<MH, TH, C::PF, RowH4>(Mv.gplane(c), pitch, w, h, x0 - C::HALO + 4 * q, y0, rows_in,
-                                                  V + (size_t)c * TH * C::VP + 4 * q, C::VP);
+                column_task_blocked<MH, C::PF, RowH4, 2>(Mv, (unsigned)c * kMbGBytes, w, h, x0 - C::HALO + 4 * q, y0, rows_in,
+                                                         V + (size_t)c * TH * C::VROW + q, C::VROW, C::NC4);
             } else {
                 const int t2 = task - 3 * C::NC4;
                 const int c = t2 / C::NC2, q = t2 - c * C::NC2;
-                column_task<MH, TH, C::PF, RowF2>(Mv.hplane(c), pitch, w, h, x0 - C::HALO + 2 * q, y0, rows_in,
-                                                  V + (size_t)(3 + c) * TH * C::VP + 2 * q, C::VP);
+                column_task_blocked<MH, C::PF, RowF2, 4>(Mv, kMbHOff + (unsigned)c * kMbHBytes, w, h, x0 - C::HALO + 2 * q, y0, rows_in,
+                                                         V + (size_t)(3 + c) * TH * C::VROW + (q & 1) * 2 * C::NC4 + (q >> 1), C::VROW, C::NC4);
             }
         } else {
             const int c = task / C::NC4, q = task - c * C::NC4;
-            column_task<MH, TH, C::PF, RowF4>(Mv.p + (size_t)c * plane, pitch, w, h, x0 - C::HALO + 4 * q, y0, rows_in,
-                                              V + (size_t)c * TH * C::VP + 4 * q, C::VP);
+            column_task_planar<MH, TH, C::PF, RowF4>(Mv.p + (size_t)c * plane, pitch, w, h, x0 - C::HALO + 4 * q, y0, rows_in,
+                                                     V + (size_t)c * TH * C::VP + 4 * q, C::VP);
         }
     }
     __syncthreads();
@@ -450,27 +580,34 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solv
     for (int k = 0; k < RG; ++k) {
         const int r = rb + NW * k;
         float gs[5][4];
+        if constexpr (RH) {
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const float4* vp = reinterpret_cast<const float4*>(V + ((size_t)c * TH + r) * C::VP) + g;
-            float vv[4 * C::NCH];
+            for (int c = 0; c < 3; ++c) hwindow4<MH, C::D, false>(V + ((size_t)c * TH + r) * C::VROW + g, C::NC4, gs[c]);
 #pragma unroll
-            for (int i = 0; i < C::NCH; ++i) {
-                const float4 t = vp[i];
-                vv[4 * i] = t.x; vv[4 * i + 1] = t.y; vv[4 * i + 2] = t.z; vv[4 * i + 3] = t.w;
+            for (int c = 3; c < 5; ++c) hwindow4<MH, C::D, true>(V + ((size_t)c * TH + r) * C::VROW + g, C::NC4, gs[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const float4* vp = reinterpret_cast<const float4*>(V + ((size_t)c * TH + r) * C::VP) + g;
+                float vv[4 * C::NCH];
+#pragma unroll
+                for (int i = 0; i < C::NCH; ++i) {
+                    const float4 t = vp[i];
+                    vv[4 * i] = t.x; vv[4 * i + 1] = t.y; vv[4 * i + 2] = t.z; vv[4 * i + 3] = t.w;
+                }
+                // common part vv[D+3 .. D+2MH], summed as two interleaved chains for ILP
+                float t0 = vv[C::D + 3], t1 = vv[C::D + 4];
+#pragma unroll
+                for (int i = C::D + 5; i + 1 <= C::D + 2 * MH; i += 2) { t0 += vv[i]; t1 += vv[i + 1]; }
+                if (((2 * MH - 2) & 1) != 0) t0 += vv[C::D + 2 * MH];
+                const float T = t0 + t1;
+                const float l2 = vv[C::D + 2], l12 = vv[C::D + 1] + l2, l012 = vv[C::D] + l12;
+                const float r1 = vv[C::D + 2 * MH + 1], r12 = r1 + vv[C::D + 2 * MH + 2], r123 = r12 + vv[C::D + 2 * MH + 3];
+                gs[c][0] = T + l012;
+                gs[c][1] = (T + l12) + r1;
+                gs[c][2] = (T + l2) + r12;
+                gs[c][3] = T + r123;
             }
-            // common part vv[D+3 .. D+2MH], summed as two interleaved chains for ILP
-            float t0 = vv[C::D + 3], t1 = vv[C::D + 4];
-#pragma unroll
-            for (int i = C::D + 5; i + 1 <= C::D + 2 * MH; i += 2) { t0 += vv[i]; t1 += vv[i + 1]; }
-            if (((2 * MH - 2) & 1) != 0) t0 += vv[C::D + 2 * MH];
-            const float T = t0 + t1;
-            const float l2 = vv[C::D + 2], l12 = vv[C::D + 1] + l2, l012 = vv[C::D] + l12;
-            const float r1 = vv[C::D + 2 * MH + 1], r12 = r1 + vv[C::D + 2 * MH + 2], r123 = r12 + vv[C::D + 2 * MH + 3];
-            gs[c][0] = T + l012;
-            gs[c][1] = (T + l12) + r1;
-            gs[c][2] = (T + l2) + r12;
-            gs[c][3] = T + r123;
         }
         solve4<RH>(gs, reg, fl[k]);
     }
@@ -531,7 +668,7 @@ __global__ void __launch_bounds__(256, FastGaussCfg<MH, TH>::CTAS) k_blur_solve_
     const TilePos tp = decode_cta(blockIdx.x, nbx, nby, a.np, a.pair_group);
     const int x0 = tp.bx * kFbTW, y0 = tp.by * TH, p = tp.p;
     const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
-    const MView<RH> Mv(const_cast<void*>(a.M), a.m_stride, p, plane);
+    const MView<RH> Mv(const_cast<void*>(a.M), a.m_stride, p, plane, pitch, w);
     float ker[MH + 1];
 #pragma unroll
     for (int i = 0; i <= MH; ++i) ker[i] = wc.ker[i];
@@ -545,25 +682,55 @@ __global__ void __launch_bounds__(256, FastGaussCfg<MH, TH>::CTAS) k_blur_solve_
     }
 
     // ---------------- phase 1: vertical Gaussian, one scalar column per task ----------------
+    const bool rows_in = (y0 - MH >= 0) && (y0 + TH + MH <= h);
     for (int task = tid; task < 5 * C::NCOL; task += 256) {
         const int c = task / C::NCOL, col = task - c * C::NCOL;
         const int gx = min(max(x0 - C::HALO + col, 0), w - 1);
         float* dst = V + (size_t)c * TH * C::VP + col;
-        auto ld = [&](int i) -> float {                               // row y0 - MH + i, clamped (replicate)
-            const int r = min(max(y0 - MH + i, 0), h - 1);
-            return Mv.load(c, (unsigned)r * pitch + (unsigned)gx);
+        auto walk = [&](auto ld) {                                    // ld(i): row y0 - MH + i of this column (replicate border)
+            float win[C::WIN];
+#pragma unroll
+            for (int i = 0; i < C::WIN; ++i) win[i] = ld(i);
+#pragma unroll
+            for (int j = 0; j < TH; ++j) {
+                // window of output row j: ring slots (j + k) % WIN for k = 0 .. 2MH, centre k = MH
+                float sacc = win[(j + MH) % C::WIN] * ker[0];
+#pragma unroll
+                for (int i = 1; i <= MH; ++i) sacc += (win[(j + MH - i) % C::WIN] + win[(j + MH + i) % C::WIN]) * ker[i];
+                dst[j * C::VP] = sacc;
+                if (j + 1 < TH) win[j % C::WIN] = ld(j + C::WIN);     // row leaving the window is replaced by the next one
+            }
         };
-        float win[C::WIN];
-#pragma unroll
-        for (int i = 0; i < C::WIN; ++i) win[i] = ld(i);
-#pragma unroll
-        for (int j = 0; j < TH; ++j) {
-            // window of output row j: ring slots (j + k) % WIN for k = 0 .. 2MH, centre k = MH
-            float sacc = win[(j + MH) % C::WIN] * ker[0];
-#pragma unroll
-            for (int i = 1; i <= MH; ++i) sacc += (win[(j + MH - i) % C::WIN] + win[(j + MH + i) % C::WIN]) * ker[i];
-            dst[j * C::VP] = sacc;
-            if (j + 1 < TH) win[j % C::WIN] = ld(j + C::WIN);         // row leaving the window is replaced by the next one
+        if constexpr (RH) {
+            // blocked matrices, TH == 16 == block height: interior tiles read rows at compile-time offsets from three pointers
+            static_assert(TH == kMbH && MH <= kMbH, "compact Gaussian tiles are the blocks of the matrices");
+            const bool is_g = c < 3;
+            const unsigned coff = is_g ? (unsigned)c * kMbGBytes + (unsigned)(gx & 127) * 2u : kMbHOff + (unsigned)(c - 3) * kMbHBytes + (unsigned)(gx & 127) * 4u;
+            if (rows_in) {
+                const char* pc = Mv.block(gx >> 7, y0 >> 4) + coff;
+                const char* pa = pc - Mv.block_row_bytes();
+                const char* pb = pc + Mv.block_row_bytes();
+                if (is_g) walk([&](int i) {
+                    const int r = i - MH;
+                    const char* q = r < 0 ? pa + (kMbH + r) * 256 : (r < kMbH ? pc + r * 256 : pb + (r - kMbH) * 256);
+                    return __half2float(__ldg(reinterpret_cast<const __half*>(q)));
+                });
+                else walk([&](int i) {
+                    const int r = i - MH;
+                    const char* q = r < 0 ? pa + (kMbH + r) * 512 : (r < kMbH ? pc + r * 512 : pb + (r - kMbH) * 512);
+                    return __ldg(reinterpret_cast<const float*>(q));
+                });
+            } else {
+                walk([&](int i) { return Mv.load(c, min(max(y0 - MH + i, 0), h - 1), gx); });
+            }
+        } else {
+            const float* src = Mv.p + (size_t)c * plane + (unsigned)gx;
+            if (rows_in) {
+                const float* pl = src + (unsigned)(y0 - MH) * pitch;
+                walk([&](int) { const float v = __ldg(pl); pl += pitch; return v; });
+            } else {
+                walk([&](int i) { return __ldg(src + (unsigned)min(max(y0 - MH + i, 0), h - 1) * pitch); });
+            }
         }
     }
     __syncthreads();
@@ -613,8 +780,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // ---- dispatch ---------------------------------------------------------------------------------------------------------
 // Half windows with a compile-time kernel: box 2..16 (winsize 4..33), Gaussian 2..16.  Tile height: compact plans 16 rows
 // (47 KB shared, 64 registers at winsize 15 -> 4 CTAs/SM: the kernel is latency/issue-bound, resident warps win over the
-// extra vertical halo); exact plans (float4 window rows) 32 rows.  The Gaussian kernel runs 24-row tiles.
-constexpr int kBoxThCompact = 16, kBoxThExact = 32, kGaussTh = 24;
+// extra vertical halo) = the blocks of the compact matrices; exact plans (float4 window rows) 32 rows, Gaussian 24.
+constexpr int kBoxThCompact = 16, kBoxThExact = 32, kGaussThCompact = 16, kGaussThExact = 24;
 inline int box_tile_th(bool r_half) { return r_half ? kBoxThCompact : kBoxThExact; }
 inline bool box_fast_supported(const WinCoef& wc, int pitch) { return !wc.gauss && wc.m >= 2 && wc.m <= 16 && (pitch % 4) == 0; }
 inline bool gauss_fast_supported(const WinCoef& wc) { return wc.gauss && wc.m >= 2 && wc.m <= 16; }
@@ -628,7 +795,8 @@ inline int box_fast_ncta(int w, int h, bool r_half) {
     const int th = box_tile_th(r_half);
     return ((w + kFbTW - 1) / kFbTW) * ((h + th - 1) / th);
 }
-inline int gauss_fast_ncta(int w, int h) { return ((w + kFbTW - 1) / kFbTW) * ((h + kGaussTh - 1) / kGaussTh); }
+inline int gauss_tile_th(bool r_half) { return r_half ? kGaussThCompact : kGaussThExact; }
+inline int gauss_fast_ncta(int w, int h, bool r_half) { const int th = gauss_tile_th(r_half); return ((w + kFbTW - 1) / kFbTW) * ((h + th - 1) / th); }
 
 // One launcher per (half window, storage); the instantiations live in tile_inst_*.cu so that they compile in parallel.
 template <int MH, bool RH>
@@ -652,19 +820,30 @@ template <int MH, bool RH>
 void launch_box_mh(const BlurSolveArgs& a, float reg, int np, const TileMaps* maps, cudaStream_t st) {
     constexpr int TH = RH ? kBoxThCompact : kBoxThExact;
     using C = FastBoxCfg<MH, TH, RH>;
-    if (smem_attr_needed<MH * 4 + (RH ? 1 : 0)>())       // once per device; a failure would surface at the launch below
-        cudaFuncSetAttribute(k_blur_solve_box<MH, RH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     const unsigned g = (unsigned)(((a.w + kFbTW - 1) / kFbTW) * ((a.h + TH - 1) / TH)) * (unsigned)np;
     static const TileMaps none{};
+    if constexpr (MH == 7 && RH) {
+        // experiment switch: BTCSFLOW_BOX_CTAS=3 runs the 85-register build (3 CTAs per SM, no spills in the tail)
+        static const int ct = [] { const char* e = getenv("BTCSFLOW_BOX_CTAS"); return e ? atoi(e) : 0; }();
+        if (ct == 3) {
+            if (smem_attr_needed<1000>())
+                cudaFuncSetAttribute(k_blur_solve_box<MH, RH, TH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+            k_blur_solve_box<MH, RH, TH, 3><<<g, 256, 72 * 1024, st>>>(a, reg, maps != nullptr, maps ? *maps : none);   // 72 KB: 3 CTAs fit, 4 do not
+            return;
+        }
+    }
+    if (smem_attr_needed<MH * 4 + (RH ? 1 : 0)>())       // once per device; a failure would surface at the launch below
+        cudaFuncSetAttribute(k_blur_solve_box<MH, RH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     k_blur_solve_box<MH, RH, TH><<<g, 256, C::SMEM, st>>>(a, reg, maps != nullptr, maps ? *maps : none);
 }
 template <int MH, bool RH>
 void launch_gauss_mh(const BlurSolveArgs& a, const WinCoef& wc, int np, cudaStream_t st) {
-    using C = FastGaussCfg<MH, kGaussTh>;
+    constexpr int TH = RH ? kGaussThCompact : kGaussThExact;
+    using C = FastGaussCfg<MH, TH>;
     if (smem_attr_needed<MH * 4 + 2 + (RH ? 1 : 0)>())
-        cudaFuncSetAttribute(k_blur_solve_gauss<MH, RH, kGaussTh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    const unsigned g = (unsigned)(((a.w + kFbTW - 1) / kFbTW) * ((a.h + kGaussTh - 1) / kGaussTh)) * (unsigned)np;
-    k_blur_solve_gauss<MH, RH, kGaussTh><<<g, 256, C::SMEM, st>>>(a, wc);
+        cudaFuncSetAttribute(k_blur_solve_gauss<MH, RH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    const unsigned g = (unsigned)(((a.w + kFbTW - 1) / kFbTW) * ((a.h + TH - 1) / TH)) * (unsigned)np;
+    k_blur_solve_gauss<MH, RH, TH><<<g, 256, C::SMEM, st>>>(a, wc);
 }
 #define BF_INSTANTIATE_TILE_MH(MH)                                                                             \
     template void launch_box_mh<MH, true>(const BlurSolveArgs&, float, int, const TileMaps*, cudaStream_t);    \
@@ -707,11 +886,9 @@ inline void launch_gauss_fast(const BlurSolveArgs& a, const WinCoef& wc, int np,
 
 #endif  // !BF_TILE_INSTANTIATE
 
-// Host side: encode the tensor maps of one scale (compact plans) for half window mh and tile height th.  M: G planes fp16
-// [pair][3][h][pitch] followed by h planes fp32 [2][h][pitch] (14 * plane bytes per pair); R: packed pixels [slot][h][pitch]
-// x 16 B.  Returns false (maps unused, per-line prefetch instead) if the driver entry point is missing or rejects the layout.
-inline bool encode_tile_maps(TileMaps* out, const void* M, const void* R, int w, int h, int pitch, size_t plane, int max_pairs,
-                             int nslots, int mh, int th) {
+// Host side: encode the R tensor maps of one scale (compact plans) for tile height th.  R: packed pixels [slot][h][pitch] x
+// 16 B.  Returns false (maps unused, per-line prefetch instead) if the driver entry point is missing or rejects the layout.
+inline bool encode_tile_maps(TileMaps* out, const void* R, int w, int h, int pitch, size_t plane, int nslots, int th) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -726,31 +903,9 @@ inline bool encode_tile_maps(TileMaps* out, const void* M, const void* R, int w,
             encode = reinterpret_cast<EncodeFn>(fn);
     }
     if (!encode || w < 4 || h < 2 || pitch % 32 != 0) return false;
-    const int halo = (mh + 3) / 4 * 4;
     const cuuint32_t ones[4] = {1, 1, 1, 1};
-    const cuuint64_t pair_bytes = (cuuint64_t)plane * 14;
-    const cuuint32_t bw = (cuuint32_t)(kFbTW + 2 * halo), bh = (cuuint32_t)(th + 2 * mh);
-    if (bw > 256 || bh > 256) return false;
-    {
-        const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, 3, (cuuint64_t)max_pairs};
-        const cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)plane * 2, pair_bytes};
-        const cuuint32_t box[4] = {bw, bh, 3, 1};
-        if (encode(&out->g, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(M), dims, strides, box, ones,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return false;
-    }
-    {
-        const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, 2, (cuuint64_t)max_pairs};
-        const cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)plane * 4, pair_bytes};
-        const cuuint32_t box[4] = {bw, bh, 2, 1};
-        void* hbase = const_cast<char*>(static_cast<const char*>(M)) + plane * 6;
-        if (encode(&out->hh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hbase, dims, strides, box, ones,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return false;
-    }
-    // R rows as chunks of 32 pixels (128 words = 512 B): a box row is one long burst, not a 16-byte pixel
+    // R rows as chunks of 32 pixels (128 words = 512 B): a box row is one long burst, not a 16-byte pixel; the innermost
+    // box coordinate is always 0 (16-byte aligned, as the bulk-tensor unit requires)
     const cuuint64_t rdims[4] = {128, (cuuint64_t)(pitch / 32), (cuuint64_t)h, (cuuint64_t)nslots};
     const cuuint64_t rstrides[3] = {512, (cuuint64_t)pitch * 16, (cuuint64_t)plane * 16};
     const cuuint32_t box0[4] = {128, (cuuint32_t)(kFbTW / 32), (cuuint32_t)th, 1};

@@ -155,14 +155,18 @@ class FlowPlan:
         if _is_torch(prev) or _is_torch(nxt):
             return self._flow_pair_torch(prev, nxt, flow)
         prev, nxt, dtype = _coerce_pair(prev, nxt, self.width, self.height)
+        use_init = bool(int(self.params["flags"]) & OPTFLOW_USE_INITIAL_FLOW)
         if flow is None:
+            if use_init:
+                raise Cv2CompatError(-1, "OPTFLOW_USE_INITIAL_FLOW needs the initial flow in `flow` (float32 [H, W, 2])")
             flow = np.empty((self.height, self.width, 2), np.float32)
             target = flow
         else:
             if not (isinstance(flow, np.ndarray) and flow.dtype == np.float32
                     and flow.shape == (self.height, self.width, 2)):
                 raise Cv2CompatError(-1, "flow must be a float32 array of shape (H, W, 2)")
-            target = flow if flow.flags.c_contiguous else np.empty(flow.shape, np.float32)
+            # in/out with OPTFLOW_USE_INITIAL_FLOW (cv2 reads the initial flow from it), otherwise only written
+            target = flow if flow.flags.c_contiguous else (np.ascontiguousarray(flow) if use_init else np.empty(flow.shape, np.float32))
         check(self._lib.bf_flow_pair_host(self._h, prev.ctypes.data, nxt.ctypes.data, dtype, prev.strides[0],
                                           target.ctypes.data, _current_stream_ptr(self.device)))
         if target is not flow:
@@ -185,6 +189,8 @@ class FlowPlan:
             nxt = nxt.contiguous()
             prev = prev.contiguous()
         if flow is None:
+            if int(self.params["flags"]) & OPTFLOW_USE_INITIAL_FLOW:
+                raise Cv2CompatError(-1, "OPTFLOW_USE_INITIAL_FLOW needs the initial flow in `flow` (float32 CUDA tensor [H, W, 2])")
             flow = torch.empty((self.height, self.width, 2), dtype=torch.float32, device=prev.device)
         elif not (flow.is_cuda and flow.dtype == torch.float32 and flow.is_contiguous()
                   and tuple(flow.shape) == (self.height, self.width, 2)):

@@ -36,11 +36,11 @@
 extern "C" {
 #endif
 
-#define BF_OPTFLOW_USE_INITIAL_FLOW 4      /* cv2.OPTFLOW_USE_INITIAL_FLOW (not supported: reference uses flags=0) */
+#define BF_OPTFLOW_USE_INITIAL_FLOW 4      /* cv2.OPTFLOW_USE_INITIAL_FLOW: bf_flow_pair* read flow_out as the initial flow */
 #define BF_OPTFLOW_FARNEBACK_GAUSSIAN 256  /* cv2.OPTFLOW_FARNEBACK_GAUSSIAN */
 
 #define BF_E_INVALID (-1)      /* bad pointer / size / parameter (cv2: error -215 assertion) */
-#define BF_E_UNSUPPORTED (-2)  /* valid for cv2 but outside this library (e.g. USE_INITIAL_FLOW, poly_n > 16) */
+#define BF_E_UNSUPPORTED (-2)  /* valid for cv2 but outside this library (e.g. poly_n > 16, winsize > 129) */
 #define BF_E_NODEVICE (-3)     /* no usable CUDA device: hard error, never a CPU fallback */
 
 #define BF_DTYPE_U8 0
@@ -113,7 +113,9 @@ void bf_launch_count_reset(void);
 /* ---- flow for one frame pair (replaces cv2.calcOpticalFlowFarneback, optical_flow.py:173) ------------ */
 
 /* prev/next: single-channel images [H, pitch_bytes], dtype BF_DTYPE_U8 or BF_DTYPE_F32.
- * flow_out: float32 [H, W, 2] C-contiguous, channel 0 = dx, 1 = dy. */
+ * flow_out: float32 [H, W, 2] C-contiguous, channel 0 = dx, 1 = dy.  With BF_OPTFLOW_USE_INITIAL_FLOW in the plan's flags it
+ * is in/out like cv2's `flow` argument: on entry the initial flow (cv2 resizes it to the coarsest scale with INTER_AREA
+ * and multiplies by that scale). */
 int bf_flow_pair(bf_plan* plan, const void* prev, const void* next, int dtype, size_t pitch_bytes,
                  float* flow_out, void* stream);
 /* Same with HOST buffers: copies both frames in, the flow out, and synchronises the stream. */

@@ -38,8 +38,8 @@ def test_invalid_params_raise_like_cv2():
         B.calcOpticalFlowFarneback(a, a[:-1], None, **B.FB_PARAMS)
     with pytest.raises(ValueError):            # 3-channel input
         B.calcOpticalFlowFarneback(np.zeros((64, 64, 3), np.uint8), np.zeros((64, 64, 3), np.uint8), None, **B.FB_PARAMS)
-    with pytest.raises(B.BtcsFlowError) as ei:   # valid for cv2, outside this library
-        B.FlowPlan(64, 64, dict(B.FB_PARAMS, flags=4))
+    with pytest.raises(B.BtcsFlowError) as ei:   # valid for cv2, outside this library (validated before any device is touched)
+        B.FlowPlan(64, 64, dict(B.FB_PARAMS, poly_n=17))
     assert ei.value.code == _lib.BF_E_UNSUPPORTED
 
 

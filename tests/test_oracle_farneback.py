@@ -122,3 +122,24 @@ def test_static_border_branch_flip_is_inherent():
     m = spec.roi_mask()
     got = fb.farneback(fr[0], fr[1], **p)
     assert abs(got[m].mean(0) - ref[m].mean(0)).max() < 1e-5
+
+
+def test_initial_flow_flag_and_inter_area():
+    """OPTFLOW_USE_INITIAL_FLOW (SURVEY 8b lists the flag; the reference passes flags=0): cv2 resizes the caller's flow to the
+    coarsest scale with INTER_AREA and multiplies by that scale.  Pins the INTER_AREA restatement and the schedule."""
+    rng = np.random.default_rng(1)
+    for (sh, sw, h, w) in ((203, 316, 25, 40), (480, 640, 60, 80), (135, 240, 68, 120), (200, 264, 69, 91), (77, 53, 77, 53)):
+        img = (rng.standard_normal((sh, sw, 2)) * 5).astype(np.float32)
+        assert np.abs(fb.resize_area(img, w, h) - cv2.resize(img, (w, h), interpolation=cv2.INTER_AREA)).max() < 2e-6
+    h, w = 203, 316
+    a, b = textured(h, w, 1), textured(h, w, 1, shift=(5.7, -3.8))
+    init = (np.stack([np.full((h, w), 5.0), np.full((h, w), -3.5)], -1) + rng.standard_normal((h, w, 2)) * 0.3).astype(np.float32)
+    for p in (dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2),
+              dict(pyr_scale=0.7, levels=2, winsize=13, iterations=2, poly_n=5, poly_sigma=1.1),
+              dict(pyr_scale=0.5, levels=0, winsize=15, iterations=2, poly_n=5, poly_sigma=1.2)):
+        ref = cv2.calcOpticalFlowFarneback(a, b, init.copy(), flags=fb.OPTFLOW_USE_INITIAL_FLOW, **p)
+        got = fb.farneback(a, b, init.copy(), flags=fb.OPTFLOW_USE_INITIAL_FLOW, **p)
+        mean, mx = epe(got, ref)
+        assert mean < 2e-6 and mx < 5e-5, (p, mean, mx)
+        if p["levels"] == 0:        # a single scale cannot reach a 6 px motion from zero: the initial flow decides the result
+            assert epe(ref, cv2.calcOpticalFlowFarneback(a, b, None, flags=0, **p))[1] > 1.0
