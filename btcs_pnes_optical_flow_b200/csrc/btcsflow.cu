@@ -375,11 +375,14 @@ int launch_polyexp(const float* I, int pitch, size_t frame_stride, int w, int h,
     return 0;
 }
 
-// BTCSFLOW_PAIR_GROUP=g: pairs per group in the CTA order of the batched kernels (farneback_common.cuh, decode_cta)
+// Pairs per group in the CTA order of the batched kernels (farneback_common.cuh, decode_cta).  8: frame p+1's coefficients
+// (R1 of pair p, R0 of pair p+1) are read from HBM once per group instead of twice -- measured DRAM reads of the finest
+// iteration launch 6.29 -> 4.44 GB, of the first update 4.13 -> 2.65 GB (ncu, profiles/r2d_pair_group_dram.txt); the kernels are
+// latency-bound, so the time moves by 1-3 % only.  BTCSFLOW_PAIR_GROUP overrides (1 = tile-major order).
 int pair_group() {
     const char* e = getenv("BTCSFLOW_PAIR_GROUP");
-    const int v = e ? atoi(e) : 1;
-    return v >= 1 && v <= 64 ? v : 1;
+    const int v = e ? atoi(e) : 8;
+    return v >= 1 && v <= 64 ? v : 8;
 }
 
 int launch_update(const bf::UpdateArgs& a0, int np, bool r_half, cudaStream_t st) {

@@ -15,6 +15,7 @@
 //   phase 3  flow is transposed through shared memory so that lanes own consecutive pixels again: coalesced R0
 //            loads, bilinear R1 gather issued one pixel ahead, M' stores; ROI sums reduced per CTA (deterministic partials).
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -200,7 +201,7 @@ __device__ __forceinline__ void vertical_box_sums(LoadFn ld, int mode, int kl, f
     typename Row::Sum s = win[0].first();
 #pragma unroll
     for (int i = 1; i < WIN; ++i) win[i].add_to(s);
-    sum_store<EDGE>(dst, s, mode, kl);
+    if (PREFIX) prefix_store<EDGE>(dst, s, mode, kl, ng); else sum_store<EDGE>(dst, s, mode, kl);
     Row pre[PF];
 #pragma unroll
     for (int i = 0; i < PF; ++i) pre[i] = ld(WIN + i);
@@ -508,9 +509,8 @@ __device__ __forceinline__ void solve4(const float gs[5][4], float reg, float2 f
     }
 }
 
-// CT: CTAs per SM the register allocation is capped for (0 = what the window size allows, FastBoxCfg::CTAS).
-template <int MH, bool RH, int TH, int CT = 0>
-__global__ void __launch_bounds__(256, CT ? CT : FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg, const bool use_maps,
+template <int MH, bool RH, int TH>
+__global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solve_box(const BlurSolveArgs a, const float reg, const bool use_maps,
                                                                                               const __grid_constant__ TileMaps maps) {
     using C = FastBoxCfg<MH, TH, RH>;
     constexpr int NT = 256, NW = 8, RG = TH / NW;
@@ -521,9 +521,9 @@ __global__ void __launch_bounds__(256, CT ? CT : FastBoxCfg<MH, TH, RH>::CTAS) k
     const int tid = threadIdx.x;
     const int w = a.w, h = a.h;
     const int nbx = (w + kFbTW - 1) / kFbTW, nby = (h + TH - 1) / TH;
+    const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
     const TilePos tp = decode_cta(blockIdx.x, nbx, nby, a.np, a.pair_group);
     const int x0 = tp.bx * kFbTW, y0 = tp.by * TH, p = tp.p;
-    const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
     const MView<RH> Mv(const_cast<void*>(a.M), a.m_stride, p, plane, pitch, w);
     BF_TRACE_STAMP(0);
 
@@ -822,16 +822,6 @@ void launch_box_mh(const BlurSolveArgs& a, float reg, int np, const TileMaps* ma
     using C = FastBoxCfg<MH, TH, RH>;
     const unsigned g = (unsigned)(((a.w + kFbTW - 1) / kFbTW) * ((a.h + TH - 1) / TH)) * (unsigned)np;
     static const TileMaps none{};
-    if constexpr (MH == 7 && RH) {
-        // experiment switch: BTCSFLOW_BOX_CTAS=3 runs the 85-register build (3 CTAs per SM, no spills in the tail)
-        static const int ct = [] { const char* e = getenv("BTCSFLOW_BOX_CTAS"); return e ? atoi(e) : 0; }();
-        if (ct == 3) {
-            if (smem_attr_needed<1000>())
-                cudaFuncSetAttribute(k_blur_solve_box<MH, RH, TH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-            k_blur_solve_box<MH, RH, TH, 3><<<g, 256, 72 * 1024, st>>>(a, reg, maps != nullptr, maps ? *maps : none);   // 72 KB: 3 CTAs fit, 4 do not
-            return;
-        }
-    }
     if (smem_attr_needed<MH * 4 + (RH ? 1 : 0)>())       // once per device; a failure would surface at the launch below
         cudaFuncSetAttribute(k_blur_solve_box<MH, RH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     k_blur_solve_box<MH, RH, TH><<<g, 256, C::SMEM, st>>>(a, reg, maps != nullptr, maps ? *maps : none);

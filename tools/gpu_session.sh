@@ -5,8 +5,7 @@ tag=${1:-run}; shift
 out=gpurun_out
 variants=("$@")
 [ ${#variants[@]} -eq 0 ] && variants=("base:")
-python -m pytest tests -m gpu -q -x 2>&1 | tail -30 > $out/${tag}_tests.log
-tail -5 $out/${tag}_tests.log
+if [ -z "$BF_SESSION_NOTESTS" ]; then python -m pytest tests -m gpu -q -x 2>&1 | tail -30 > $out/${tag}_tests.log; tail -5 $out/${tag}_tests.log; fi
 for v in "${variants[@]}"; do
   name=${v%%:*}; envs=${v#*:}
   env $(echo $envs | tr ',' ' ') python bench.py --steps 3 --warmup 2 --no-exact --no-parity > $out/${tag}_bench_$name.log 2>&1
@@ -18,11 +17,7 @@ try:
 except Exception as e: print("$name failed", e)
 PY
 done
+if [ -n "$BF_SESSION_NCU" ]; then
 ncu --set full --clock-control none --import-source on --kernel-name regex:k_blur_solve_box --launch-skip 20 --launch-count 4 \
     -o $out/${tag}_box python bench.py --steps 1 --warmup 1 --no-exact --no-parity > $out/${tag}_ncu.log 2>&1
-BTCSFLOW_PAIR_GROUP=8 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    --kernel-name regex:"k_blur_solve_box|k_update" --launch-skip 24 --launch-count 8 --csv --log-file $out/${tag}_g8_dram.csv \
-    python bench.py --steps 1 --warmup 1 --no-exact --no-parity > /dev/null 2>&1
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    --kernel-name regex:"k_blur_solve_box|k_update" --launch-skip 24 --launch-count 8 --csv --log-file $out/${tag}_g1_dram.csv \
-    python bench.py --steps 1 --warmup 1 --no-exact --no-parity > /dev/null 2>&1
+fi

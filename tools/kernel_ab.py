@@ -41,6 +41,7 @@ for rep in range(2):                      # every variant twice, interleaved, to
         s = out[0].double().cpu().numpy()
         if base is None: base = s
         d = float(np.nanmax(np.abs(s - base)))
-        print(f"{v or 'default':40s} step {np.median(ms):7.2f} ms ({P / np.median(ms) * 1e3:6.0f} pairs/s)  dominant {pr['total_ms'] / max(pr['launches'], 1):.4f} ms"
+        st = {k: round(x["ms"] / max(x["launches"], 1), 3) for k, x in pr["stages"].items()}
+        print(f"{v or 'default':40s} step {np.median(ms):7.2f} ms ({P / np.median(ms) * 1e3:6.0f} pairs/s)  avg launch ms {st}"
               f"  series diff vs first {d:.2e}", flush=True)
         plan.close()
