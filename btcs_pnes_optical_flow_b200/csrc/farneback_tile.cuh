@@ -40,10 +40,10 @@ struct FastBoxCfg {
     // row = 4 planes x NC4 groups
     static constexpr int VROW = RH ? 4 * NC4 : VP;             // floats per (channel, row)
     static constexpr int V_FLOATS = 5 * TH * VROW;
-    static constexpr int NTASK = RH ? 3 * NC4 + 2 * NC2 : 5 * NC4;   // phase-1 column tasks per tile
+    static constexpr int NTASK = RH ? 3 * NC4 + 2 * NC2 : 5 * NC2;   // phase-1 column tasks per tile (exact: two fp32 columns each)
     static constexpr int PF = TH >= 32 ? 8 : 4;                // register prefetch depth in phase 1
     // CTAs per SM: what registers (window = WIN rows x 2 registers compact, x 4 exact) and shared memory allow
-    static constexpr int WREG = WIN * (RH ? 2 : 4);
+    static constexpr int WREG = WIN * 2;
     static constexpr int CTAS_REG = WREG <= 30 ? 4 : (WREG <= 46 ? 3 : (WREG <= 84 ? 2 : 1));
     static constexpr size_t SMEM = (size_t)(V_FLOATS + 64) * sizeof(float);
     static constexpr int CTAS_SMEM = (int)((227u * 1024u) / (SMEM + 1024u));
@@ -565,9 +565,9 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solv
                                                          V + (size_t)(3 + c) * TH * C::VROW + (q & 1) * 2 * C::NC4 + (q >> 1), C::VROW, C::NC4);
             }
         } else {
-            const int c = task / C::NC4, q = task - c * C::NC4;
-            column_task_planar<MH, TH, C::PF, RowF4>(Mv.p + (size_t)c * plane, pitch, w, h, x0 - C::HALO + 4 * q, y0, rows_in,
-                                                     V + (size_t)c * TH * C::VP + 4 * q, C::VP);
+            const int c = task / C::NC2, q = task - c * C::NC2;
+            column_task_planar<MH, TH, C::PF, RowF2>(Mv.p + (size_t)c * plane, pitch, w, h, x0 - C::HALO + 2 * q, y0, rows_in,
+                                                     V + (size_t)c * TH * C::VP + 2 * q, C::VP);
         }
     }
     __syncthreads();
@@ -781,7 +781,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Half windows with a compile-time kernel: box 2..16 (winsize 4..33), Gaussian 2..16.  Tile height: compact plans 16 rows
 // (47 KB shared, 64 registers at winsize 15 -> 4 CTAs/SM: the kernel is latency/issue-bound, resident warps win over the
 // extra vertical halo) = the blocks of the compact matrices; exact plans (float4 window rows) 32 rows, Gaussian 24.
-constexpr int kBoxThCompact = 16, kBoxThExact = 32, kGaussThCompact = 16, kGaussThExact = 24;
+constexpr int kBoxThCompact = 16, kBoxThExact = 16, kGaussThCompact = 16, kGaussThExact = 24;
 inline int box_tile_th(bool r_half) { return r_half ? kBoxThCompact : kBoxThExact; }
 inline bool box_fast_supported(const WinCoef& wc, int pitch) { return !wc.gauss && wc.m >= 2 && wc.m <= 16 && (pitch % 4) == 0; }
 inline bool gauss_fast_supported(const WinCoef& wc) { return wc.gauss && wc.m >= 2 && wc.m <= 16; }
