@@ -430,7 +430,7 @@ def run_ours(args, cfg, spec, params):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_total, launches, prof, pc1 = timed(args.steps, args.warmup, launch_device, tail_device, prof_plan=plan)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _, _, pc1_h = timed(args.steps, max(1, args.warmup // 2) if args.warmup else 0, launch_host, tail_host)
+    ms_e2e, _, _, pc1_h = timed(args.steps, args.warmup, launch_host, tail_host)
 
     if rank == 0:
         pairs = world * P * args.steps

@@ -273,7 +273,8 @@ struct bf_plan {
     float* tmp = nullptr;       // [F][H][pitch0]
     void* M[2] = {nullptr, nullptr};   // matrices ping-pong: f32 planes, or fp16 planes on compact plans
     float* axes = nullptr;      // [B][4]
-    float* partial = nullptr;   // [B][max_rois][ncta][4]
+    float* partial = nullptr;   // [B][max_rois][ncta][kRoiVals]
+    uint8_t* roi_class = nullptr;   // [max_rois][ncta]: class of every tile of the last launch (k_roi_tile_class), per series call
     int ncta_max = 0;
     size_t bytes = 0;
     // host-staging path
@@ -528,6 +529,7 @@ int prof_end(bf_plan* p, cudaStream_t st) {
 }
 
 struct RoiCtx {
+    bool classes_ready = false;      // p->roi_class holds the tile classes of these masks (computed at the first batch)
     const uint8_t* masks = nullptr;  // [n_roi][H][W]
     int n_roi = 0;
     const double* ex = nullptr;      // device [T][2]
@@ -540,7 +542,7 @@ struct RoiCtx {
 // flow_out: dense [np][H][W][2] or NULL.  roi: optional ROI reduction into roi->out rows t0+1+q.
 // init_flow: OPTFLOW_USE_INITIAL_FLOW -- dense [np][H][W][2] flow the coarsest scale starts from (cv2: INTER_AREA resize
 // times the scale); may alias flow_out (read at the coarsest scale, written by the last launch).
-int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cudaStream_t st, const float* init_flow = nullptr) {
+int run_pairs(bf_plan* p, int t0, int np, float* flow_out, RoiCtx* roi, cudaStream_t st, const float* init_flow = nullptr) {
     const int I = p->prm.iterations;
     const int nsc = (int)p->sc.size();
     const int slot0 = t0 % p->F;
@@ -617,6 +619,19 @@ int run_pairs(bf_plan* p, int t0, int np, float* flow_out, const RoiCtx* roi, cu
                 if (want_roi) {
                     a.masks = roi->masks; a.n_roi = roi->n_roi; a.mask_stride = (size_t)p->H * p->W; a.mask_pitch = p->W;
                     a.axes = p->axes; a.partial = p->partial;
+                    // tile classes of the masks (tile kernels only), once per series call
+                    const BlurKernel bk = choose_blur_kernel(a, p->wc, p->use_fast);
+                    if (bk == BK_TILE || bk == BK_GAUSS) {
+                        const int th = bk == BK_TILE ? bf::box_tile_th(p->r_half) : bf::gauss_tile_th(p->r_half);
+                        const int nbx = cdiv(s.w, bf::kFbTW), nby = cdiv(s.h, th);
+                        if (!roi->classes_ready) {
+                            bf::k_roi_tile_class<<<dim3(cdiv(nbx * nby, 4), roi->n_roi), 128, 0, st>>>(roi->masks, roi->n_roi, p->W, p->H, bf::kFbTW, th,
+                                                                                                      nbx, nby, p->roi_class);
+                            LAUNCH_CHECK();
+                            roi->classes_ready = true;
+                        }
+                        a.roi_class = p->roi_class;
+                    }
                 }
             }
             if ((rc = prof_begin(p, finest ? (last ? BF_PROF_ITER_LAST : BF_PROF_ITER_UPDATE) : BF_PROF_COARSE, np, st))) return rc;
@@ -791,6 +806,7 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
     if ((rc = plan_alloc(p, &p->axes, (size_t)p->B * 4))) return cleanup_fail(rc);
     p->ncta_max = std::max(cdiv(fine.w, bf::kBsTW) * cdiv(fine.h, bf::kBsTH), cdiv(fine.w, bf::kFbTW) * cdiv(fine.h, 16));
     if ((rc = plan_alloc(p, &p->partial, (size_t)p->B * std::max(max_rois, 1) * p->ncta_max * bf::kRoiVals))) return cleanup_fail(rc);
+    if ((rc = plan_alloc(p, &p->roi_class, (size_t)std::max(max_rois, 1) * p->ncta_max))) return cleanup_fail(rc);
     if (cudaDeviceSynchronize() != cudaSuccess) return cleanup_fail(fail(2, "plan initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out = p;
     return 0;
@@ -804,7 +820,7 @@ int bf_plan_destroy(bf_plan* p) {
         cudaFree(s.fix); cudaFree(s.fiy); cudaFree(s.fax); cudaFree(s.fay);
         cudaFree(s.I); cudaFree(s.R); cudaFree(s.flow); cudaFree(s.tmpk);
     }
-    cudaFree(p->tmp); cudaFree(p->M[0]); cudaFree(p->M[1]); cudaFree(p->axes); cudaFree(p->partial);
+    cudaFree(p->tmp); cudaFree(p->M[0]); cudaFree(p->M[1]); cudaFree(p->axes); cudaFree(p->partial); cudaFree(p->roi_class);
     cudaFree(p->ia_xofs); cudaFree(p->ia_xidx); cudaFree(p->ia_xwgt); cudaFree(p->ia_yofs); cudaFree(p->ia_yidx); cudaFree(p->ia_ywgt);
     cudaFree(p->stage[0]); cudaFree(p->stage[1]); cudaFree(p->stage_flow);
     cudaFree(p->pair_in[0]); cudaFree(p->pair_in[1]); cudaFree(p->pair_flow);

@@ -380,6 +380,9 @@ struct BlurSolveArgs {
     const uint8_t* masks; int n_roi; size_t mask_stride; int mask_pitch;
     const float* axes;  // [pair][4] = ex0, ex1, ey0, ey1
     float* partial;
+    // optional: class of every (roi, tile) of this launch's tile grid -- 0 = no ROI pixel in the tile, 1 = all of the tile's
+    // pixels, 2 = mixed (k_roi_tile_class); NULL = treat every tile as mixed
+    const uint8_t* roi_class;
 };
 
 // accurate a*b - c*d (Kahan): the structure-tensor determinant cancels heavily where the window holds

@@ -385,6 +385,27 @@ __global__ void k_roi_finalize(const float* __restrict__ partial, int n_pairs, i
     for (int k = 0; k < 3; ++k) o[k] = (ok && s[3 + k] > 0.0) ? (float)(s[k] / s[3 + k]) : nanv;
 }
 
+// Class of every (roi, tile) for tiles of tw x th pixels: 0 = the mask is zero on the whole tile, 1 = non-zero on all of its
+// in-image pixels, 2 = mixed.  Once per series call; lets the last iteration skip the per-pixel mask loads (a full-frame ROI,
+// config C2, is class 1 everywhere; a small ROI leaves most tiles at class 0).  One warp per tile.
+__global__ void __launch_bounds__(128) k_roi_tile_class(const uint8_t* __restrict__ masks, int n_roi, int W, int H, int tw, int th,
+                                                        int nbx, int nby, uint8_t* __restrict__ cls) {
+    const int tile = blockIdx.x * 4 + (threadIdx.x >> 5), roi = blockIdx.y, lane = threadIdx.x & 31;
+    if (tile >= nbx * nby) return;
+    const int bx = tile % nbx, by = tile / nbx;
+    const int x0 = bx * tw, y0 = by * th, x1 = min(x0 + tw, W), y1 = min(y0 + th, H);
+    const uint8_t* m = masks + (size_t)roi * W * H;
+    bool any = false, all = true;
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0 + lane; x < x1; x += 32) {
+            const bool on = m[(size_t)y * W + x] != 0;
+            any |= on; all &= on;
+        }
+    any = __any_sync(0xffffffffu, any);
+    all = __all_sync(0xffffffffu, all);
+    if (lane == 0) cls[(size_t)roi * nbx * nby + tile] = all ? 1 : (any ? 2 : 0);
+}
+
 // OPTFLOW_USE_INITIAL_FLOW: the caller's full-resolution flow resized to the coarsest scale with cv2's INTER_AREA weights
 // (tables built on the host: for destination index d the source taps ofs[d] .. ofs[d+1]-1) and multiplied by the scale.
 struct AreaTab { const int* ofs; const int* idx; const float* wgt; };

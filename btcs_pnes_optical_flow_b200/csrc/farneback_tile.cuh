@@ -431,16 +431,35 @@ __device__ __forceinline__ void tile_tail(const BlurSolveArgs& a, const float2* 
         const float e00 = ax[0], e01 = ax[1], e10 = ax[2], e11 = ax[3];
         const int x = x0 + tail_c0;
         for (int roi = 0; roi < a.n_roi; ++roi) {
-            const uint8_t* mk = a.masks + (size_t)roi * a.mask_stride + (size_t)(y0 + tail_r0) * a.mask_pitch + x;
+            const int cls = a.roi_class ? a.roi_class[(size_t)roi * ncta + cta] : 2;        // CTA-uniform
+            float* dst = a.partial + (((size_t)p * a.n_roi + roi) * ncta + cta) * kRoiVals;
+            if (cls == 0) {                                                                 // no ROI pixel in this tile
+                if (tid < 6) dst[tid] = 0.f;
+                continue;
+            }
             RoiAcc acc;
+            if (cls == 1) {                                                                 // every in-image pixel counts: no mask loads
 #pragma unroll 4
-            for (int i = 0; i < N; ++i) {
-                if (x < w && y0 + tail_r0 + i < h && mk[(size_t)i * a.mask_pitch] != 0) {
-                    const float2 f = F[(tail_r0 + i) * kFbTW + tail_c0];
-                    acc.add(f.x * e00 + f.y * e01, f.x * e10 + f.y * e11);
+                for (int i = 0; i < N; ++i) {
+                    if (x < w && y0 + tail_r0 + i < h) {
+                        const float2 f = F[(tail_r0 + i) * kFbTW + tail_c0];
+                        acc.add(f.x * e00 + f.y * e01, f.x * e10 + f.y * e11);
+                    }
+                }
+            } else {
+                const uint8_t* mk = a.masks + (size_t)roi * a.mask_stride + (size_t)(y0 + tail_r0) * a.mask_pitch + x;
+                bool on[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) on[i] = x < w && y0 + tail_r0 + i < h && mk[(size_t)i * a.mask_pitch] != 0;   // loads first
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    if (on[i]) {
+                        const float2 f = F[(tail_r0 + i) * kFbTW + tail_c0];
+                        acc.add(f.x * e00 + f.y * e01, f.x * e10 + f.y * e11);
+                    }
                 }
             }
-            roi_cta_store(acc, s_red, a.partial + (((size_t)p * a.n_roi + roi) * ncta + cta) * kRoiVals);
+            roi_cta_store(acc, s_red, dst);
         }
     }
 }

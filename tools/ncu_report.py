@@ -45,9 +45,22 @@ def main(rep, pixels, which):
         if lg or sh:
             n_sm = 148
             print(f"   LSU wavefronts per pixel: shared {sh * n_sm / pixels:.2f} + global/local {lg * n_sm / pixels:.2f}")
-        # source page of the same launch (the page lists every profiled launch in order)
-        if w < len(starts):
-            a, b = starts[w], starts[w + 1] if w + 1 < len(starts) else len(src)
+        # source page of the same launch: the page does not list the launches in the order of the raw page, so take the
+        # block whose executed-instruction total matches this launch's smsp__inst_executed.sum
+        want = f(col.get("smsp__inst_executed.sum", "0"))
+        best, best_err = None, None
+        for bi in range(len(starts)):
+            a, b = starts[bi], starts[bi + 1] if bi + 1 < len(starts) else len(src)
+            blk = list(csv.reader(io.StringIO("\n".join(src[a:b]))))
+            if len(blk) < 3 or "Instructions Executed" not in blk[1]:
+                continue
+            wi = blk[1].index("Instructions Executed")
+            tot = sum(f(x[wi]) for x in blk[2:] if len(x) > wi)
+            err = abs(tot - want)
+            if best_err is None or err < best_err:
+                best, best_err = (a, b), err
+        if best is not None:
+            a, b = best
             srows = list(csv.reader(io.StringIO("\n".join(src[a:b]))))
             sh_, data = srows[1], [x for x in srows[2:] if len(x) > 5]
             ix = {h: i for i, h in enumerate(sh_)}
