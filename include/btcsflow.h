@@ -69,15 +69,16 @@ typedef struct bf_plan bf_plan;
  * max_rois = number of ROI masks a series call may carry (>= 0).  device = CUDA ordinal. */
 int bf_plan_create(const bf_params* params, int width, int height, int max_pairs, int max_rois, int device,
                    bf_plan** out);
-/* Same with flags.  BF_PLAN_EXACT_F32: keep the polynomial coefficients as float32 planes (the default packs them in
- * 16 bytes per pixel when poly_n is 5 or 7: linear terms float32, quadratic terms fp16 -- storage only, arithmetic is
- * fp32; <= 5e-4 px against cv2 -- which is range-safe for uint8 frames only).  float32 input frames require an exact
+/* Same with flags.  BF_PLAN_EXACT_F32: keep the polynomial coefficients and the update matrices as float32 planes.  The
+ * default for poly_n 5 or 7 is the compact storage: coefficients in 16 bytes per pixel (linear terms float32, quadratic
+ * terms fp16) and matrices as fp16 G + float32 h formed from the rounded G -- storage only, arithmetic is fp32; ~1e-5 px
+ * mean / < 1e-3 px max against cv2 -- which is range-safe for uint8 frames only.  float32 input frames require an exact
  * plan. */
 #define BF_PLAN_EXACT_F32 1u
 int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pairs, int max_rois, int device,
                       unsigned flags, bf_plan** out);
 int bf_plan_destroy(bf_plan* plan);
-/* Narrowest stored polynomial coefficient in bits: 16 (packed pixel) or 32 (exact planes). */
+/* Narrowest stored polynomial coefficient in bits: 16 (compact plan) or 32 (exact plan). */
 int bf_plan_coeff_storage(const bf_plan* plan);
 /* Bytes of device scratch the plan owns. */
 size_t bf_plan_workspace_bytes(const bf_plan* plan);

@@ -40,9 +40,10 @@ for case in range(n_cases):
             d = np.sqrt(((got - ref) ** 2).sum(-1)); mean, inner, edge = float(d.mean()), 0.0, float(d.max())
         else:
             mean, inner, edge = epe_banded(got, ref, band)
-        # compact plans: a fifth of the north_star gates on the interior (narrow Gaussian windows average less: up to 5e-3)
-        ok = mean <= 1e-3 and inner <= 1e-2 and edge <= 0.25 and np.isfinite(got).all()
-        if exact: ok = ok and inner <= 1e-4           # fp32 storage: ~1e-6 inside; the band can still hold a branch flip (rounding order)
+        # moving content over the whole frame (no static border): the north_star max gate is held on the WHOLE frame, border
+        # band included, by both plans; interior far tighter
+        ok = mean <= 1e-3 and inner <= 2e-3 and edge <= 0.05 and np.isfinite(got).all()
+        if exact: ok = ok and inner <= 1e-4           # fp32 storage: ~1e-6 inside
         worst.append((inner, edge, mean, case, h, w, exact, p))
         if not ok:
             bad += 1
