@@ -173,8 +173,13 @@ struct UpdateArgs {
 // third of them index arithmetic and constant loads; ncu, profiles/).
 constexpr int kUpdRows = 4;   // 8 rows: 74 registers, slower (18.1 vs 17.3 ms per 128 pairs)
 
+// Compact plans: the kernel uses no shared memory, so L1 is large (256 KB per SM) -- every thread first requests the lines
+// its rows will gather (R0 pixel, the two tap rows of R1) into L1 and then walks its rows one after the other, L1-hit
+// loads, no register double-buffering of the taps: 40 registers, 6 CTAs per SM.  (The software-pipelined form it replaces
+// -- next row's gather in flight in registers, 64 registers, 4 CTAs/SM -- took 1.45 ms per 64-pair 1080p launch, this one
+// 1.23 ms; the kernel is latency-bound and responds to resident warps; profiles/r2_experiments.txt.)
 template <bool RH>
-__global__ void __launch_bounds__(256, 4) k_update(const UpdateArgs a) {
+__global__ void __launch_bounds__(256, RH ? 6 : 4) k_update(const UpdateArgs a) {
     // block = 64 columns x (4 x kUpdRows) rows; 1-D grid in decode_cta order
     const TilePos tp = decode_cta(blockIdx.x, (a.w + 63) / 64, (a.h + 4 * kUpdRows - 1) / (4 * kUpdRows), a.np, a.pair_group);
     const int x = tp.bx * 64 + threadIdx.x;
@@ -237,7 +242,6 @@ __global__ void __launch_bounds__(256, 4) k_update(const UpdateArgs a) {
     }
     if (!want_m) return;
     if constexpr (RH) {
-        // packed coefficients: row k+1's taps are in flight while row k is computed (update_issue_h / update_finish_h)
         const uint4* R0h = static_cast<const uint4*>(R0);
         const uint4* R1h = static_cast<const uint4*>(R1);
         // the thread's kUpdRows rows lie in one block of M (yb is a multiple of kUpdRows, which divides the block height):
@@ -246,18 +250,28 @@ __global__ void __launch_bounds__(256, 4) k_update(const UpdateArgs a) {
         char* blk = Mo.block(x >> 7, yb >> 4);
         char* pg = blk + MView<true>::g_off(yb & 15, x & 127);
         char* ph = blk + MView<true>::h_off(yb & 15, x & 127);
-        const uint4* q = R0h + (unsigned)min(yb, h - 1) * pitch + (unsigned)x;
-        UpdTaps A, B;
-        update_issue_h(q, R1h, pitch, w, h, x, min(yb, h - 1), fl[0].x, fl[0].y, A);
+        // (the always-true runtime test keeps the compiler from carrying this loop's tap coordinates into the next one:
+        // merged, the two loops spill 190 bytes at 40 registers)
+        if (a.np > 0) {
 #pragma unroll
-        for (int k = 0; k < kUpdRows; k += 2) {
-            update_issue_h(R0h + (unsigned)min(yb + k + 1, h - 1) * pitch + (unsigned)x, R1h, pitch, w, h, x, min(yb + k + 1, h - 1), fl[k + 1].x, fl[k + 1].y, B);
+            for (int k = 0; k < kUpdRows; ++k) {
+                const int yy = min(yb + k, h - 1);
+                const int x1 = __float2int_rd((float)x + fl[k].x), y1 = __float2int_rd((float)yy + fl[k].y);
+                const int cx = max(min(x1, w - 2), 0), cy = max(min(y1, h - 2), 0);
+                const uint4* pa = R1h + (unsigned)cy * pitch + (unsigned)cx;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + pitch));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(R0h + (unsigned)yy * pitch + (unsigned)x));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kUpdRows; ++k) {
+            const int yy = min(yb + k, h - 1);
+            UpdTaps T;
+            update_issue_h(R0h + (unsigned)yy * pitch + (unsigned)x, R1h, pitch, w, h, x, yy, fl[k].x, fl[k].y, T);
             MOut<true> m;
-            if (inner) update_finish_h<false>(A, w, h, x, yb + k, m); else update_finish_h<true>(A, w, h, x, yb + k, m);
+            if (inner) update_finish_h<false>(T, w, h, x, yb + k, m); else update_finish_h<true>(T, w, h, x, yb + k, m);
             if (yb + k < h) MView<true>::store_at(pg + k * (kMbW * 2), ph + k * (kMbW * 4), m);
-            if (k + 2 < kUpdRows) update_issue_h(R0h + (unsigned)min(yb + k + 2, h - 1) * pitch + (unsigned)x, R1h, pitch, w, h, x, min(yb + k + 2, h - 1), fl[k + 2].x, fl[k + 2].y, A);
-            if (inner) update_finish_h<false>(B, w, h, x, yb + k + 1, m); else update_finish_h<true>(B, w, h, x, yb + k + 1, m);
-            if (yb + k + 1 < h) MView<true>::store_at(pg + (k + 1) * (kMbW * 2), ph + (k + 1) * (kMbW * 4), m);
         }
     } else {
 #pragma unroll
