@@ -651,28 +651,95 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solv
 // ---------------------------------------------------------------------------------------------------
 // k_blur_solve_gauss<MH>: the same fused iteration for OPTFLOW_FARNEBACK_GAUSSIAN (separable float32
 // Gaussian window, sigma = 0.3*MH, replicate borders) -- config C4 runs winsize 21 (MH = 10).  No running sums here:
-// every output is a (2MH+1)-tap weighted sum.  Phase 1 walks one scalar column per thread with the (2MH+1)-row window in
-// registers (fully unrolled static ring); phase 2 reads 4+2MH values per channel with LDS.128 and evaluates 4 outputs;
-// summation order is cv2's: centre tap first, then symmetric pairs (x[-i] + x[+i]) * ker[i].
+// every output is a (2MH+1)-tap weighted sum, and the kernel is bound by the ISSUE of those FP32 operations (ncu: the
+// scalar version spent 280 + 130 instructions per pixel in the two passes).  Both passes therefore work on PAIRS of fp32
+// values with the packed sm_100a instructions (fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2: two IEEE fp32 operations
+// per issue slot, coefficient operand broadcast), in "scatter" form: every loaded value is multiplied into the outputs it
+// contributes to and then dropped, so neither pass keeps a window in registers.
+//   pairs      A = (G11, G12) and B = (h1, h2) of one pixel; the fifth channel (G22) is paired over two adjacent columns
+//              in the vertical pass and runs scalar in the horizontal one
+//   phase 1    one task = one column of a channel pair (or a column pair of G22): TH + 2MH loads, TH accumulator pairs,
+//              <= (2MH+1) FFMA2 per load; results to shared memory as float2 (channel-interleaved planes A and B, plain G22)
+//   phase 2    one thread = 4 adjacent outputs x TH/8 rows: LDS.128 = two columns of a channel pair, 4 accumulator pairs
+//   shared     planes A/B store their two-column chunks even chunks first, odd chunks from chunk HOFF on: the lanes of
+//              phase 2 (chunk stride 2) then read consecutive 16-byte chunks and the float2 stores of phase 1 stay
+//              conflict-free (HOFF = 4 mod 8)
+// Summation runs in row / column order (cv2: centre, then symmetric pairs): an fp32 reordering, ~1e-7 relative.
 // ---------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 up2(f32x2_t v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 template <int MH, int TH>
 struct FastGaussCfg {
     static constexpr int HALO = (MH + 3) / 4 * 4;
     static constexpr int D = HALO - MH;
-    static constexpr int NCOL = kFbTW + 2 * HALO;
-    static constexpr int VP = NCOL + 4;
+    static constexpr int NCOL = kFbTW + 2 * HALO;               // multiple of 8
+    static constexpr int VP = NCOL + 4;                         // row pitch of the plain (G22) plane, floats
     static constexpr int WIN = 2 * MH + 1;
-    static constexpr int NCH = (D + 2 * MH + 3) / 4 + 1;
+    static constexpr int NCH = (D + 2 * MH + 3) / 4 + 1;        // LDS.128 per row of the plain plane
+    // pair planes: chunk = 2 columns x 2 channels = 16 bytes
+    static constexpr int NE = NCOL / 4;                         // even (= odd) chunks per row
+    static constexpr int HOFF = NE + ((12 - NE % 8) % 8);       // first odd chunk: >= NE and = 4 (mod 8)
+    static constexpr int ROWCH = HOFF + NE;                     // chunks per row
+    static constexpr int DE = D & ~1, E = D - DE;               // phase 2 starts at the even column 4g + DE
+    static constexpr int NCHK = (E + 2 * MH + 4 + 1) / 2;       // chunks per thread and row
     static constexpr int RG = TH / 8;
-    static constexpr int V_FLOATS = 5 * TH * VP;
-    static constexpr size_t SMEM = (size_t)(V_FLOATS + 64) * sizeof(float);
+    static constexpr int PAIR_FLOATS = TH * ROWCH * 4;          // one pair plane
+    static constexpr int V_FLOATS = 2 * PAIR_FLOATS + TH * VP;
+    static constexpr size_t SMEM = (size_t)(V_FLOATS + 64 + 32) * sizeof(float);   // + reduction scratch + taps (edge tiles)
     static constexpr int CTAS_SMEM = (int)((227u * 1024u) / (SMEM + 1024u));
-    static constexpr int CTAS_REG = WIN <= 23 ? 3 : 2;
+    static constexpr int CTAS_REG = 3;
     static constexpr int CTAS = CTAS_REG < CTAS_SMEM ? CTAS_REG : (CTAS_SMEM < 1 ? 1 : CTAS_SMEM);
+    static constexpr int NTASK_A = (NCOL + 31) / 32 * 32;       // task ranges start on warp boundaries (no divergence)
+    static constexpr int NTASK = 2 * NTASK_A + NCOL / 2;
     static_assert(MH >= 2 && MH <= 16, "half window out of range for the fast path");
     static_assert(TH % 8 == 0, "tile height must be a multiple of 8");
+    static_assert(NCOL % 8 == 0 && HOFF % 8 == 4 && HOFF >= NE, "chunk layout");
+    static_assert(4 * 31 + DE + 2 * NCHK <= NCOL, "phase 2 must stay inside the tile row");
     static_assert((size_t)TH * kFbTW * sizeof(float2) <= (size_t)V_FLOATS * sizeof(float), "F must fit in V");
 };
+
+// Vertical (2MH+1)-tap sums of TH consecutive outputs from TH + 2MH inputs, in pairs.  ld(i) = packed input row i of the
+// window (row y0 - MH + i), st(j, v) = output row j.  Everything unrolls: the tap of input i in output j is ker[|i-MH-j|].
+template <int MH, int TH, typename Ld, typename St>
+__device__ __forceinline__ void gauss_vertical2(Ld ld, St st, const f32x2_t (&k2)[MH + 1]) {
+    f32x2_t acc[TH];
+#pragma unroll
+    for (int i = 0; i < TH + 2 * MH; ++i) {
+        const f32x2_t v = ld(i);
+#pragma unroll
+        for (int j = 0; j < TH; ++j) {
+            const int d = i - MH - j;
+            if (d == -MH) acc[j] = mul2(v, k2[MH]);
+            else if (d > -MH && d <= MH) acc[j] = fma2(v, k2[d < 0 ? -d : d], acc[j]);
+        }
+        if (i >= 2 * MH) st(i - 2 * MH, acc[i - 2 * MH]);
+    }
+}
+
+// Phase-1 task of a tile whose window leaves the image at the top or bottom (rows clamped = replicate border).  Kept out of
+// line: inlined, the compiler hoists the 2 x (TH + 2MH) clamped row addresses of this rare path above the branch and
+// spills them in EVERY thread (ncu: 11 local stores per pixel, 44 B/px of DRAM writes).
+template <int MH, bool RH, int TH, bool PAIR_COLS>
+__device__ __noinline__ void gauss_vertical_edge_task(const MView<RH> Mv, int h, int y0, int c0, int gx, bool lo_y, bool hi_y,
+                                                      float* dst, int dst_pitch, const float* __restrict__ ker) {
+    // PAIR_COLS: channel c0 at columns gx, gx + 1 (gx even; the halves picked by lo_y / hi_y); else channels c0, c0 + 1 at gx
+    f32x2_t k2[MH + 1];
+#pragma unroll
+    for (int i = 0; i <= MH; ++i) k2[i] = pk2(ker[i], ker[i]);
+    gauss_vertical2<MH, TH>(
+        [&](int i) {
+            const int y = min(max(y0 - MH + i, 0), h - 1);
+            return PAIR_COLS ? pk2(Mv.load(c0, y, gx), Mv.load(c0, y, gx + 1)) : pk2(Mv.load(c0, y, gx), Mv.load(c0 + 1, y, gx));
+        },
+        [&](int j, f32x2_t v) {
+            const float2 t = up2(v);
+            *reinterpret_cast<float2*>(dst + j * dst_pitch) = PAIR_COLS ? make_float2(lo_y ? t.y : t.x, hi_y ? t.y : t.x) : t;
+        }, k2);
+}
 
 template <int MH, bool RH, int TH>
 __global__ void __launch_bounds__(256, FastGaussCfg<MH, TH>::CTAS) k_blur_solve_gauss(const BlurSolveArgs a, const WinCoef wc) {
@@ -688,9 +755,9 @@ __global__ void __launch_bounds__(256, FastGaussCfg<MH, TH>::CTAS) k_blur_solve_
     const int x0 = tp.bx * kFbTW, y0 = tp.by * TH, p = tp.p;
     const unsigned pitch = (unsigned)a.pitch, plane = (unsigned)a.plane_stride;
     const MView<RH> Mv(const_cast<void*>(a.M), a.m_stride, p, plane, pitch, w);
-    float ker[MH + 1];
+    f32x2_t k2[MH + 1];
 #pragma unroll
-    for (int i = 0; i <= MH; ++i) ker[i] = wc.ker[i];
+    for (int i = 0; i <= MH; ++i) k2[i] = pk2(wc.ker[i], wc.ker[i]);
 
     const void* R0 = nullptr;
     const void* R1 = nullptr;
@@ -700,55 +767,99 @@ __global__ void __launch_bounds__(256, FastGaussCfg<MH, TH>::CTAS) k_blur_solve_
         prefetch_r_block<RH, TH>(R0, R1, plane, pitch, w, h, x0, y0, tid, 256);
     }
 
-    // ---------------- phase 1: vertical Gaussian, one scalar column per task ----------------
+    // ---------------- phase 1: vertical Gaussian on pairs ----------------
     const bool rows_in = (y0 - MH >= 0) && (y0 + TH + MH <= h);
-    for (int task = tid; task < 5 * C::NCOL; task += 256) {
-        const int c = task / C::NCOL, col = task - c * C::NCOL;
-        const int gx = min(max(x0 - C::HALO + col, 0), w - 1);
-        float* dst = V + (size_t)c * TH * C::VP + col;
-        auto walk = [&](auto ld) {                                    // ld(i): row y0 - MH + i of this column (replicate border)
-            float win[C::WIN];
-#pragma unroll
-            for (int i = 0; i < C::WIN; ++i) win[i] = ld(i);
-#pragma unroll
-            for (int j = 0; j < TH; ++j) {
-                // window of output row j: ring slots (j + k) % WIN for k = 0 .. 2MH, centre k = MH
-                float sacc = win[(j + MH) % C::WIN] * ker[0];
-#pragma unroll
-                for (int i = 1; i <= MH; ++i) sacc += (win[(j + MH - i) % C::WIN] + win[(j + MH + i) % C::WIN]) * ker[i];
-                dst[j * C::VP] = sacc;
-                if (j + 1 < TH) win[j % C::WIN] = ld(j + C::WIN);     // row leaving the window is replaced by the next one
-            }
-        };
-        if constexpr (RH) {
-            // blocked matrices, TH == 16 == block height: interior tiles read rows at compile-time offsets from three pointers
-            static_assert(TH == kMbH && MH <= kMbH, "compact Gaussian tiles are the blocks of the matrices");
-            const bool is_g = c < 3;
-            const unsigned coff = is_g ? (unsigned)c * kMbGBytes + (unsigned)(gx & 127) * 2u : kMbHOff + (unsigned)(c - 3) * kMbHBytes + (unsigned)(gx & 127) * 4u;
-            if (rows_in) {
-                const char* pc = Mv.block(gx >> 7, y0 >> 4) + coff;
-                const char* pa = pc - Mv.block_row_bytes();
-                const char* pb = pc + Mv.block_row_bytes();
-                if (is_g) walk([&](int i) {
-                    const int r = i - MH;
-                    const char* q = r < 0 ? pa + (kMbH + r) * 256 : (r < kMbH ? pc + r * 256 : pb + (r - kMbH) * 256);
-                    return __half2float(__ldg(reinterpret_cast<const __half*>(q)));
-                });
-                else walk([&](int i) {
-                    const int r = i - MH;
-                    const char* q = r < 0 ? pa + (kMbH + r) * 512 : (r < kMbH ? pc + r * 512 : pb + (r - kMbH) * 512);
-                    return __ldg(reinterpret_cast<const float*>(q));
-                });
+    float* const ker_s = smem + C::V_FLOATS + 64;                  // taps for the out-of-line edge path (block-uniform branch)
+    if (!rows_in) {
+        if (tid <= MH) ker_s[tid] = wc.ker[tid];
+        __syncthreads();
+    }
+    float* const VA = V;
+    float* const VB = V + C::PAIR_FLOATS;
+    float* const VS = V + 2 * C::PAIR_FLOATS;
+    for (int task = tid; task < C::NTASK; task += 256) {
+        if (task < 2 * C::NTASK_A) {
+            // channel pair A (task < NTASK_A) or B of one column
+            const bool isB = task >= C::NTASK_A;
+            const int col = isB ? task - C::NTASK_A : task;
+            if (col >= C::NCOL) continue;
+            const int gx = min(max(x0 - C::HALO + col, 0), w - 1);
+            const int chunk = col >> 1;
+            float* dst = (isB ? VB : VA) + (((chunk >> 1) + (chunk & 1) * C::HOFF) * 4 + (col & 1) * 2);
+            auto st = [&](int j, f32x2_t v) { *reinterpret_cast<f32x2_t*>(dst + j * (C::ROWCH * 4)) = v; };
+            const int c0 = isB ? 3 : 0;
+            if constexpr (RH) {
+                static_assert(TH == kMbH && MH <= kMbH, "compact Gaussian tiles are the blocks of the matrices");
+                if (rows_in) {
+                    // blocked matrices: rows at compile-time offsets from three pointers (block above, this one, below)
+                    const char* pc = Mv.block(gx >> 7, y0 >> 4);
+                    const unsigned brow = Mv.block_row_bytes();
+                    if (!isB) {
+                        pc += (unsigned)(gx & 127) * 2u;
+                        const char* pa = pc - brow;
+                        const char* pb = pc + brow;
+                        gauss_vertical2<MH, TH>([&](int i) {
+                            const int r = i - MH;
+                            const char* q = r < 0 ? pa + (kMbH + r) * 256 : (r < kMbH ? pc + r * 256 : pb + (r - kMbH) * 256);
+                            return pk2(h2f(__ldg(reinterpret_cast<const unsigned short*>(q))),
+                                       h2f(__ldg(reinterpret_cast<const unsigned short*>(q + kMbGBytes))));
+                        }, st, k2);
+                    } else {
+                        pc += kMbHOff + (unsigned)(gx & 127) * 4u;
+                        const char* pa = pc - brow;
+                        const char* pb = pc + brow;
+                        gauss_vertical2<MH, TH>([&](int i) {
+                            const int r = i - MH;
+                            const char* q = r < 0 ? pa + (kMbH + r) * 512 : (r < kMbH ? pc + r * 512 : pb + (r - kMbH) * 512);
+                            return pk2(__ldg(reinterpret_cast<const float*>(q)), __ldg(reinterpret_cast<const float*>(q + kMbHBytes)));
+                        }, st, k2);
+                    }
+                } else {
+                    gauss_vertical_edge_task<MH, RH, TH, false>(Mv, h, y0, c0, gx, false, false, dst, C::ROWCH * 4, ker_s);
+                }
             } else {
-                walk([&](int i) { return Mv.load(c, min(max(y0 - MH + i, 0), h - 1), gx); });
+                if (rows_in) {
+                    const float* pl = Mv.p + (size_t)c0 * plane + (unsigned)gx + (unsigned)(y0 - MH) * pitch;
+                    gauss_vertical2<MH, TH>([&](int) { const f32x2_t v = pk2(__ldg(pl), __ldg(pl + plane)); pl += pitch; return v; }, st, k2);
+                } else {
+                    gauss_vertical_edge_task<MH, RH, TH, false>(Mv, h, y0, c0, gx, false, false, dst, C::ROWCH * 4, ker_s);
+                }
             }
         } else {
-            const float* src = Mv.p + (size_t)c * plane + (unsigned)gx;
-            if (rows_in) {
-                const float* pl = src + (unsigned)(y0 - MH) * pitch;
-                walk([&](int) { const float v = __ldg(pl); pl += pitch; return v; });
+            // G22 (channel 2), two adjacent columns: the pair is loaded from the even column xe; columns clamped to the image
+            // (replicate) pick their half after the sums (the filter is linear)
+            const int cp = task - 2 * C::NTASK_A;                   // column pair: tile columns 2cp, 2cp + 1
+            const int x = x0 - C::HALO + 2 * cp;
+            const int cl = min(max(x, 0), w - 1), chh = min(max(x + 1, 0), w - 1);
+            const int xe = cl & ~1;
+            const bool lo_y = (cl & 1) != 0, hi_y = (chh - xe) != 0;
+            float* dst = VS + 2 * cp;
+            auto st = [&](int j, f32x2_t v) {
+                const float2 t = up2(v);
+                *reinterpret_cast<float2*>(dst + j * C::VP) = make_float2(lo_y ? t.y : t.x, hi_y ? t.y : t.x);
+            };
+            if constexpr (RH) {
+                auto cvt = [](unsigned u) { unsigned short l, hh; split_h2(u, l, hh); return pk2(h2f(l), h2f(hh)); };
+                if (rows_in) {
+                    const char* pc = Mv.block(xe >> 7, y0 >> 4) + 2 * kMbGBytes + (unsigned)(xe & 127) * 2u;
+                    const unsigned brow = Mv.block_row_bytes();
+                    const char* pa = pc - brow;
+                    const char* pb = pc + brow;
+                    gauss_vertical2<MH, TH>([&](int i) {
+                        const int r = i - MH;
+                        const char* q = r < 0 ? pa + (kMbH + r) * 256 : (r < kMbH ? pc + r * 256 : pb + (r - kMbH) * 256);
+                        return cvt(__ldg(reinterpret_cast<const unsigned*>(q)));
+                    }, st, k2);
+                } else {
+                    gauss_vertical_edge_task<MH, RH, TH, true>(Mv, h, y0, 2, xe, lo_y, hi_y, dst, C::VP, ker_s);
+                }
             } else {
-                walk([&](int i) { return __ldg(src + (unsigned)min(max(y0 - MH + i, 0), h - 1) * pitch); });
+                if (rows_in) {
+                    const float* pl = Mv.p + (size_t)2 * plane + (unsigned)xe + (unsigned)(y0 - MH) * pitch;
+                    gauss_vertical2<MH, TH>([&](int) { const float2 t = __ldg(reinterpret_cast<const float2*>(pl)); pl += pitch; return pk2(t.x, t.y); }, st, k2);
+                } else {
+                    gauss_vertical_edge_task<MH, RH, TH, true>(Mv, h, y0, 2, xe, lo_y, hi_y, dst, C::VP, ker_s);
+                }
             }
         }
     }
@@ -762,22 +873,53 @@ __global__ void __launch_bounds__(256, FastGaussCfg<MH, TH>::CTAS) k_blur_solve_
         const int r = rb + 8 * k;
         float gs[5][4];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const float4* vp = reinterpret_cast<const float4*>(V + ((size_t)c * TH + r) * C::VP) + g;
-            float vv[4 * C::NCH];
+        for (int pl = 0; pl < 2; ++pl) {
+            // thread g: columns 4g + DE .. of the row = chunks 2g + DE/2 + i; chunk parity is compile-time
+            const ulonglong2* rowp = reinterpret_cast<const ulonglong2*>((pl ? VB : VA) + (size_t)r * (C::ROWCH * 4)) + g;
+            f32x2_t acc[4];
 #pragma unroll
-            for (int i = 0; i < C::NCH; ++i) {
-                const float4 q4 = vp[i];
-                vv[4 * i] = q4.x; vv[4 * i + 1] = q4.y; vv[4 * i + 2] = q4.z; vv[4 * i + 3] = q4.w;
+            for (int i = 0; i < C::NCHK; ++i) {
+                constexpr int S = C::DE / 2;
+                const int ch = S + i;
+                const ulonglong2 q = rowp[(ch >> 1) + (ch & 1) * C::HOFF];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const f32x2_t v = half ? q.y : q.x;
+                    const int l = 2 * i + half;                      // column 4g + DE + l
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int d = l - (C::E + MH + j);
+                        if (d == -MH) acc[j] = mul2(v, k2[MH]);
+                        else if (d > -MH && d <= MH) acc[j] = fma2(v, k2[d < 0 ? -d : d], acc[j]);
+                    }
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int ci = C::HALO + j;
-                float sacc = vv[ci] * ker[0];
-#pragma unroll
-                for (int i = 1; i <= MH; ++i) sacc += (vv[ci - i] + vv[ci + i]) * ker[i];
-                gs[c][j] = sacc;
+                const float2 t = up2(acc[j]);
+                gs[pl ? 3 : 0][j] = t.x;
+                gs[pl ? 4 : 1][j] = t.y;
             }
+        }
+        {
+            const float4* vp = reinterpret_cast<const float4*>(VS + (size_t)r * C::VP) + g;
+            float acc[4];
+#pragma unroll
+            for (int i = 0; i < C::NCH; ++i) {
+                const float4 q4 = vp[i];
+                const float vv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int d = 4 * i + e - (C::HALO + j);     // column 4g + 4i + e against output centre 4g + HALO + j
+                        if (d == -MH) acc[j] = vv[e] * wc.ker[MH];
+                        else if (d > -MH && d <= MH) acc[j] = fmaf(vv[e], wc.ker[d < 0 ? -d : d], acc[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gs[2][j] = acc[j];
         }
         solve4<RH>(gs, 1e-3f, fl[k]);
     }
@@ -800,7 +942,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Half windows with a compile-time kernel: box 2..16 (winsize 4..33), Gaussian 2..16.  Tile height: compact plans 16 rows
 // (47 KB shared, 64 registers at winsize 15 -> 4 CTAs/SM: the kernel is latency/issue-bound, resident warps win over the
 // extra vertical halo) = the blocks of the compact matrices; exact plans (float4 window rows) 32 rows, Gaussian 24.
-constexpr int kBoxThCompact = 16, kBoxThExact = 16, kGaussThCompact = 16, kGaussThExact = 24;
+constexpr int kBoxThCompact = 16, kBoxThExact = 16, kGaussThCompact = 16, kGaussThExact = 16;
 inline int box_tile_th(bool r_half) { return r_half ? kBoxThCompact : kBoxThExact; }
 inline bool box_fast_supported(const WinCoef& wc, int pitch) { return !wc.gauss && wc.m >= 2 && wc.m <= 16 && (pitch % 4) == 0; }
 inline bool gauss_fast_supported(const WinCoef& wc) { return wc.gauss && wc.m >= 2 && wc.m <= 16; }

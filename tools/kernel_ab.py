@@ -11,12 +11,15 @@ import btcs_pnes_optical_flow_b200 as B
 from btcs_pnes_optical_flow_b200 import synthetic as syn
 
 variants = sys.argv[1:] or [""]
-spec, params = syn.config_spec("C2")
-P, NIT = 128, 7
+CFG = os.environ.get("KAB_CONFIG", "C2")          # KAB_CONFIG=C4 KAB_PAIRS=32 KAB_MAXPAIRS=16 for the 4K Gaussian case
+spec, params = syn.config_spec(CFG)
+P, NIT = int(os.environ.get("KAB_PAIRS", "128")), 7
+MAXP = int(os.environ.get("KAB_MAXPAIRS", "64"))
+EXACT = os.environ.get("KAB_EXACT", "0") == "1"
 spec.T = P + 1
 dev = torch.device("cuda")
 frames = syn.make_clip(spec, dev, 0, P + 1)
-mask = torch.ones((1080, 1920), dtype=torch.uint8, device=dev)
+mask = torch.ones((spec.H, spec.W), dtype=torch.uint8, device=dev)
 base = None
 touched = set()
 for rep in range(2):                      # every variant twice, interleaved, to see drift
@@ -26,7 +29,7 @@ for rep in range(2):                      # every variant twice, interleaved, to
             k, val = kv.split("=")
             os.environ[k] = val
             touched.add(k)
-        plan = B.FlowPlan(1920, 1080, params, max_pairs=64)
+        plan = B.FlowPlan(spec.W, spec.H, params, max_pairs=MAXP, exact=EXACT)
         plan.profile(True)
         ms = []
         for it in range(NIT):
