@@ -27,6 +27,13 @@ struct FastPeCfg {
     static constexpr size_t SMEM = (size_t)3 * kFbTH * VP * sizeof(float);
 };
 
+// two adjacent 16-byte pixels as one 256-bit store; p must be 32-byte aligned
+__device__ __forceinline__ void store_px2(uint4* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+                 "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 // Horizontal pass of the polynomial expansion from the shared vertical-pass result + the 5-coefficient store.
 template <int N, bool RH>
 __device__ __forceinline__ void polyexp_horizontal_store(const float* smem, int x0, int y0, int f, int pitch, int w, int h,
@@ -38,6 +45,7 @@ __device__ __forceinline__ void polyexp_horizontal_store(const float* smem, int 
     const int slot = (slot0 + f) % nslots;
     float* Rb = RH ? nullptr : static_cast<float*>(Rv) + (size_t)slot * slot_stride;
     uint4* Rh = RH ? static_cast<uint4*>(Rv) + (size_t)slot * slot_stride : nullptr;
+    const bool wide = (reinterpret_cast<uintptr_t>(Rh) & 31) == 0;      // pitch and x are multiples of 4 pixels: rows stay 32-byte aligned
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         const int r = rb + 8 * k;
@@ -80,9 +88,16 @@ __device__ __forceinline__ void polyexp_horizontal_store(const float* smem, int 
         if (RH) {
             if (y < h) {
                 uint4* op = Rh + (size_t)y * pitch + x;
+                if (x + 3 < w && wide) {
+                    // the thread's 4 pixels are 64 contiguous bytes: two 256-bit stores (sm_100a) touch each 128-byte line once
+                    // per instruction pair instead of once per pixel (lane stride 64 B)
+                    store_px2(op, pack_r(o[0][0], o[1][0], o[2][0], o[3][0], o[4][0]), pack_r(o[0][1], o[1][1], o[2][1], o[3][1], o[4][1]));
+                    store_px2(op + 2, pack_r(o[0][2], o[1][2], o[2][2], o[3][2], o[4][2]), pack_r(o[0][3], o[1][3], o[2][3], o[3][3], o[4][3]));
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (x + j < w) op[j] = pack_r(o[0][j], o[1][j], o[2][j], o[3][j], o[4][j]);
+                    for (int j = 0; j < 4; ++j)
+                        if (x + j < w) op[j] = pack_r(o[0][j], o[1][j], o[2][j], o[3][j], o[4][j]);
+                }
             }
         } else if (y < h && x < w) {
             float* op = Rb + (size_t)y * pitch + x;
