@@ -363,7 +363,7 @@ int launch_pyramid(bf_plan* p, const ScaleInfo& s, const T* src, size_t pitch_by
 int launch_polyexp(const float* I, int pitch, size_t frame_stride, int w, int h, void* R, size_t plane_stride,
                    size_t slot_stride, int slot0, int nslots, int nf, const bf::PolyCoef& pc, bool allow_fast, bool r_half,
                    cudaStream_t st) {
-    if (allow_fast && bf::polyexp_fast_supported(pc.n, pitch) && bf::polyexp_fast_aligned(R, plane_stride, slot_stride)) {
+    if (allow_fast && bf::polyexp_fast_supported(pc.n, pitch) && bf::polyexp_fast_aligned(R, plane_stride, slot_stride, I, frame_stride)) {
         bf::launch_polyexp_fast(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, nf, pc, r_half, st);
         LAUNCH_CHECK();
         return 0;
@@ -441,26 +441,11 @@ int launch_blur_solve(const bf::BlurSolveArgs& a0, const bf::WinCoef& wc, int np
 template <typename T>
 int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_bytes, int tf, int nf,
                   cudaStream_t st) {
-    bool fused_l0 = false;
     if (p->use_fast && bf::pyr_h_smem_bytes(p->W) <= 160 * 1024) {
         // level 0: exact 3x3 stencil; coarser levels: one multi-level horizontal pass + per-level vertical pass
         bf::PyrHArgs pa{};
-        // level 0 (scale 1): optionally fuse the blur into the polynomial expansion (BTCSFLOW_FUSED_L0=1).  Off by default:
-        // measured 5385 vs 5744 pairs/s at 1080p -- the byte-wise tile load + shared-memory blur stage and the drop from 3
-        // to 2 CTAs/SM cost more than the saved level-image round trip (profiles/r1f_phase_experiments.txt).
-        const ScaleInfo& fine = p->sc.back();
-        const size_t fine_slot = p->r_half ? fine.plane : 5 * fine.plane;
-        const char* fz = getenv("BTCSFLOW_FUSED_L0");
-        fused_l0 = fz && fz[0] == '1' && bf::polyexp_fast_supported(p->pc.n, fine.pitch) &&
-                   bf::polyexp_fast_aligned(fine.R, fine.plane, fine_slot);
         for (auto& s : p->sc) {
             if (s.k == 0) {
-                if (fused_l0) {
-                    bf::launch_polyexp_l0<T>(frames, pitch_bytes, frame_bytes, s.pitch, s.w, s.h, s.R, s.plane, fine_slot, tf % p->F,
-                                             p->F, nf, p->pc, p->r_half, st);
-                    LAUNCH_CHECK();
-                    continue;
-                }
                 dim3 g(cdiv(p->W, bf::kL0TW), cdiv(p->H, bf::kL0TH), nf);
                 bf::k_level0_blur<T><<<g, 128, 0, st>>>(frames, pitch_bytes, frame_bytes, p->W, p->H, s.I, s.pitch, s.plane);
                 LAUNCH_CHECK();
@@ -497,7 +482,6 @@ int expand_frames(bf_plan* p, const T* frames, size_t pitch_bytes, size_t frame_
         }
     }
     for (auto& s : p->sc) {
-        if (s.k == 0 && fused_l0) continue;
         int rc = launch_polyexp(s.I, s.pitch, s.plane, s.w, s.h, s.R, s.plane, p->r_half ? s.plane : 5 * s.plane, tf % p->F,
                                 p->F, nf, p->pc, p->use_fast, p->r_half, st);
         if (rc) return rc;

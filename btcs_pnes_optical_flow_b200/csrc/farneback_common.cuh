@@ -202,6 +202,15 @@ __device__ __forceinline__ unsigned pack_h2_sat(float lo, float hi) { unsigned d
 __device__ __forceinline__ unsigned short f2h_sat(float v) { unsigned short d; asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(d) : "f"(v)); return d; }
 __device__ __forceinline__ float h2f(unsigned short h) { float d; asm("cvt.f32.f16 %0, %1;" : "=f"(d) : "h"(h)); return d; }
 
+// ---- packed fp32 pairs (sm_100a FFMA2 / FMUL2: two IEEE fp32 operations per issue slot; a scalar operand is broadcast when
+// both halves of a pair are the same register) ---------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 up2(f32x2_t v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // ---- packed polynomial coefficients: 16 bytes per pixel, one 128-bit load per bilinear tap ------------------------
 // Storage format only.  The linear terms b (whose frame-to-frame DIFFERENCE drives the flow) stay fp32; the quadratic
 // terms A, which only enter through averages, are fp16: (b_y f32, b_x f32, (A_yy, A_xx) f16x2, (A_xy, 0) f16x2).  It turns

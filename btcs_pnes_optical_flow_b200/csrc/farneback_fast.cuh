@@ -9,22 +9,37 @@
 namespace bf {
 
 // ---------------------------------------------------------------------------------------------------
-// k_polyexp<N>: separable polynomial expansion with compile-time poly_n.  Tile 128 x 32, 256 threads.
-//   vertical pass   thread per (column, 8-row group): coalesced 32-bit loads straight from global (rows clamped =
-//                   replicate), the 8+2N values live in registers, taps are compile-time constants-bank reads
-//   horizontal pass thread per 4 consecutive outputs: conflict-free LDS.128, 128-bit coalesced plane stores
+// k_polyexp<N>: separable polynomial expansion with compile-time poly_n.  Tile 128 x 24, 256 threads.
+// The kernel is bound by the issue of its FP32 operations (ncu: 72 % of 133 instructions per pixel were FFMA / FADD /
+// FMUL), so both passes work on packed fp32 pairs (FFMA2 / FADD2, farneback_common.cuh):
+//   vertical pass   task = (column pair, 8-row group): 64-bit loads straight from global (rows clamped = replicate), the
+//                   8 + 2N row pairs live in registers; per tap one packed add, one packed subtract, three packed FMAs
+//   shared memory   plane P01 = (t0, t1) interleaved per column, stored as 16-byte chunks of two columns, even chunks
+//                   first and odd chunks from chunk HOFF on (HOFF = 4 mod 8: conflict-free STS.128 here and LDS.128 with a
+//                   lane stride of two chunks in the horizontal pass); plane P2 = t2 plain
+//   horizontal pass thread = 4 adjacent outputs, scatter form: every loaded column is multiplied into the outputs it reaches
+//                   -- (b1, b3) += g (t0, t1), (b2, b6) += +-xg (t0, t1) as pairs, b4 += xxg t0 and b5 += g t2 scalar -- so
+//                   no window is held in registers; the 4 packed pixels leave as two 256-bit stores
+// Sums run in row / column order (cv2: centre, then symmetric pairs): an fp32 reordering of the coefficients, ~1e-7 rel.
 // ---------------------------------------------------------------------------------------------------
+constexpr int kPeFastTH = 24;
 template <int N>
 struct FastPeCfg {
-    // HALO = N exactly: a 4-output group then reads the 2N + 4 values it needs from float4 chunk 0 onwards, all of them
-    // LDS.128.  With the halo rounded up to 8 the first and last value sat alone in their chunks and were fetched by scalar
-    // LDS with a 16-byte lane stride (4-way bank conflicts, a quarter of the kernel's shared-memory wavefronts; ncu).
-    static constexpr int HALO = N;
+    static constexpr int HALO = (N + 1) & ~1;                   // even: column pairs start on even columns
+    static constexpr int D = HALO - N;
     static constexpr int NCOL = kFbTW + 2 * HALO;
-    static constexpr int VP = (NCOL + 3) / 4 * 4 + 4;
-    static constexpr int RG = 4, RPG = kFbTH / RG;             // row groups, rows per group
-    static constexpr int NCH = (HALO + N + 3) / 4 + 1;
-    static constexpr size_t SMEM = (size_t)3 * kFbTH * VP * sizeof(float);
+    static constexpr int NPAIR = NCOL / 2;                      // column pairs = 16-byte chunks of P01 per row
+    static constexpr int NE = (NPAIR + 1) / 2;                  // even chunks
+    static constexpr int HOFF = NE + ((12 - NE % 8) % 8);       // first odd chunk: >= NE and = 4 (mod 8)
+    static constexpr int ROWCH = HOFF + NPAIR / 2;              // chunks per P01 row
+    static constexpr int VP = (NCOL + 3) / 4 * 4;               // P2 row pitch (floats)
+    static constexpr int RPG = 8, RG = kPeFastTH / RPG;             // rows per task, row groups
+    static constexpr int NCH = (D + 2 * N + 3) / 4 + 1;         // 4-column groups read by a thread of the horizontal pass
+    static constexpr int P01_FLOATS = kPeFastTH * ROWCH * 4;
+    static constexpr size_t SMEM = (size_t)(P01_FLOATS + kPeFastTH * VP) * sizeof(float);
+    static_assert(NCOL % 4 == 0 && HOFF % 8 == 4 && HOFF >= NE, "chunk layout");
+    static_assert(4 * 31 + 4 * NCH <= NCOL, "horizontal pass must stay inside the tile row");
+    static_assert(RG * NPAIR <= 256, "one vertical task per thread");
 };
 
 // two adjacent 16-byte pixels as one 256-bit store; p must be 32-byte aligned
@@ -34,55 +49,136 @@ __device__ __forceinline__ void store_px2(uint4* p, const uint4& a, const uint4&
                  : "memory");
 }
 
-// Horizontal pass of the polynomial expansion from the shared vertical-pass result + the 5-coefficient store.
 template <int N, bool RH>
-__device__ __forceinline__ void polyexp_horizontal_store(const float* smem, int x0, int y0, int f, int pitch, int w, int h,
-                                                         void* __restrict__ Rv, size_t plane_stride, size_t slot_stride,
-                                                         int slot0, int nslots, const PolyCoef& pc) {
+__global__ void __launch_bounds__(256, N <= 5 ? 4 : 3) k_polyexp(const float* __restrict__ I, int pitch, size_t frame_stride, int w,
+                                                                 int h, void* __restrict__ Rv, size_t plane_stride,
+                                                                 size_t slot_stride, int slot0, int nslots, const PolyCoef pc) {
     using C = FastPeCfg<N>;
+    extern __shared__ __align__(16) float smem[];
+    float* const P01 = smem;
+    float* const P2 = smem + C::P01_FLOATS;
     const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kPeFastTH, f = blockIdx.z;
+    const float* img = I + (size_t)f * frame_stride;
+
+    // ---------------- vertical pass: column pairs ----------------
+    if (tid < C::RG * C::NPAIR) {
+        const int rg = tid / C::NPAIR, cp = tid - rg * C::NPAIR;
+        // tile columns 2cp, 2cp + 1 = image columns x, x + 1 (x even); columns outside the image replicate the border
+        // column: the pair is loaded from the even column xe and the halves are picked after the sums (the filter is linear)
+        const int x = x0 - C::HALO + 2 * cp;
+        const int cl = min(max(x, 0), w - 1), ch = min(max(x + 1, 0), w - 1);
+        const int xe = cl & ~1;
+        const bool lo_y = (cl & 1) != 0, hi_y = (ch - xe) != 0;
+        const bool straight = !lo_y && hi_y;                        // both columns inside: no selection
+        const int yb = y0 + rg * C::RPG - N;
+        f32x2_t v[C::RPG + 2 * N];
+#pragma unroll
+        for (int i = 0; i < C::RPG + 2 * N; ++i) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(img + (size_t)min(max(yb + i, 0), h - 1) * pitch + xe));
+            v[i] = pk2(t.x, t.y);
+        }
+        f32x2_t g2[N + 1], xg2[N + 1], xxg2[N + 1];
+#pragma unroll
+        for (int k = 0; k <= N; ++k) { g2[k] = pk2(pc.g[k], pc.g[k]); xg2[k] = pk2(pc.xg[k], pc.xg[k]); xxg2[k] = pk2(pc.xxg[k], pc.xxg[k]); }
+        const f32x2_t m1 = pk2(-1.f, -1.f);
+        const int chunk = cp;
+        float* d01 = P01 + ((size_t)(rg * C::RPG) * C::ROWCH + (chunk >> 1) + (chunk & 1) * C::HOFF) * 4;
+        float* d2 = P2 + (size_t)(rg * C::RPG) * C::VP + 2 * cp;
+#pragma unroll
+        for (int j = 0; j < C::RPG; ++j) {
+            f32x2_t t0 = mul2(v[j + N], g2[0]), t1, t2;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const f32x2_t up = v[j + N - k], dn = v[j + N + k];
+                const f32x2_t pp = add2(up, dn);
+                const f32x2_t dd = fma2(up, m1, dn);                // dn - up (exact: the product by -1 does not round)
+                t0 = fma2(pp, g2[k], t0);
+                t1 = k == 1 ? mul2(dd, xg2[k]) : fma2(dd, xg2[k], t1);
+                t2 = k == 1 ? mul2(pp, xxg2[k]) : fma2(pp, xxg2[k], t2);
+            }
+            float2 a = up2(t0), b = up2(t1), c = up2(t2);
+            if (!straight) {
+                a = make_float2(lo_y ? a.y : a.x, hi_y ? a.y : a.x);
+                b = make_float2(lo_y ? b.y : b.x, hi_y ? b.y : b.x);
+                c = make_float2(lo_y ? c.y : c.x, hi_y ? c.y : c.x);
+            }
+            *reinterpret_cast<float4*>(d01 + (size_t)j * (C::ROWCH * 4)) = make_float4(a.x, b.x, a.y, b.y);
+            *reinterpret_cast<float2*>(d2 + (size_t)j * C::VP) = c;
+        }
+    }
+    __syncthreads();
+
+    // ---------------- horizontal pass + coefficient store ----------------
     const int g = tid & 31, rb = tid >> 5;
     const int slot = (slot0 + f) % nslots;
     float* Rb = RH ? nullptr : static_cast<float*>(Rv) + (size_t)slot * slot_stride;
     uint4* Rh = RH ? static_cast<uint4*>(Rv) + (size_t)slot * slot_stride : nullptr;
     const bool wide = (reinterpret_cast<uintptr_t>(Rh) & 31) == 0;      // pitch and x are multiples of 4 pixels: rows stay 32-byte aligned
+    f32x2_t g2[N + 1], pxg2[N + 1], nxg2[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; ++k) { g2[k] = pk2(pc.g[k], pc.g[k]); pxg2[k] = pk2(pc.xg[k], pc.xg[k]); nxg2[k] = pk2(-pc.xg[k], -pc.xg[k]); }
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kPeFastTH / 8; ++k) {
         const int r = rb + 8 * k;
         const int y = y0 + r, x = x0 + 4 * g;
-        float vv[3][4 * C::NCH];
+        // thread g: tile columns 4g .. 4g + 4 NCH - 1 = chunks 2g + i; output j sits at tile column HALO + 4g + j
+        const ulonglong2* row01 = reinterpret_cast<const ulonglong2*>(P01 + (size_t)r * (C::ROWCH * 4)) + g;
+        const float4* row2 = reinterpret_cast<const float4*>(P2 + (size_t)r * C::VP) + g;
+        f32x2_t b13[4], b26[4];
+        float b4[4], b5[4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float4* vp = reinterpret_cast<const float4*>(smem + ((size_t)c * kFbTH + r) * C::VP) + g;
+        for (int i = 0; i < 2 * C::NCH; ++i) {
+            const ulonglong2 q = row01[(i >> 1) + (i & 1) * C::HOFF];
+            float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((i & 1) == 0) q2 = row2[i >> 1];
 #pragma unroll
-            for (int i = 0; i < C::NCH; ++i) {
-                const float4 t = vp[i];
-                vv[c][4 * i] = t.x; vv[c][4 * i + 1] = t.y; vv[c][4 * i + 2] = t.z; vv[c][4 * i + 3] = t.w;
+            for (int hf = 0; hf < 2; ++hf) {
+                const int l = 2 * i + hf;                             // tile column 4g + l
+                const f32x2_t v01 = hf ? q.y : q.x;
+                const float v0 = up2(v01).x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int d = l - (C::HALO + j);                  // column offset from output j
+                    if (d < -N || d > N) continue;
+                    const int ad = d < 0 ? -d : d;
+                    if (d == -N) {
+                        b13[j] = mul2(v01, g2[N]);
+                        b26[j] = mul2(v01, nxg2[N]);
+                        b4[j] = v0 * pc.xxg[N];
+                    } else {
+                        b13[j] = fma2(v01, g2[ad], b13[j]);
+                        if (d != 0) {
+                            b26[j] = fma2(v01, d < 0 ? nxg2[ad] : pxg2[ad], b26[j]);
+                            b4[j] = fmaf(v0, pc.xxg[ad], b4[j]);
+                        }
+                    }
+                }
+            }
+            // t2 of the same 4 columns (every second chunk step)
+            if ((i & 1) == 0) {
+                const float vv[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int d = 4 * (i >> 1) + e - (C::HALO + j);
+                        if (d < -N || d > N) continue;
+                        const int ad = d < 0 ? -d : d;
+                        b5[j] = d == -N ? vv[e] * pc.g[N] : fmaf(vv[e], pc.g[ad], b5[j]);
+                    }
+                }
             }
         }
         float o[5][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int ci = C::HALO + j;
-            float b1 = vv[0][ci] * pc.g[0], b3 = vv[1][ci] * pc.g[0], b5 = vv[2][ci] * pc.g[0];
-            float b2 = 0.f, b4 = 0.f, b6 = 0.f;
-#pragma unroll
-            for (int t = 1; t <= N; ++t) {
-                const float p0 = vv[0][ci + t], m0 = vv[0][ci - t];
-                const float p1 = vv[1][ci + t], m1 = vv[1][ci - t];
-                const float p2 = vv[2][ci + t], m2 = vv[2][ci - t];
-                const float tg = p0 + m0;
-                b1 = fmaf(tg, pc.g[t], b1);
-                b4 = fmaf(tg, pc.xxg[t], b4);
-                b2 = fmaf(p0 - m0, pc.xg[t], b2);
-                b3 = fmaf(p1 + m1, pc.g[t], b3);
-                b6 = fmaf(p1 - m1, pc.xg[t], b6);
-                b5 = fmaf(p2 + m2, pc.g[t], b5);
-            }
+            const float2 s13 = up2(b13[j]), s26 = up2(b26[j]);
+            const float b1 = s13.x, b3 = s13.y, b2 = s26.x, b6 = s26.y;
             o[0][j] = b3 * pc.ig11;
             o[1][j] = b2 * pc.ig11;
-            o[2][j] = fmaf(b1, pc.ig03, b5 * pc.ig33);
-            o[3][j] = fmaf(b1, pc.ig03, b4 * pc.ig33);
+            o[2][j] = fmaf(b1, pc.ig03, b5[j] * pc.ig33);
+            o[3][j] = fmaf(b1, pc.ig03, b4[j] * pc.ig33);
             o[4][j] = b6 * pc.ig55;
         }
         if (RH) {
@@ -114,44 +210,6 @@ __device__ __forceinline__ void polyexp_horizontal_store(const float* smem, int 
             }
         }
     }
-}
-
-template <int N, bool RH>
-__global__ void __launch_bounds__(256, 4) k_polyexp(const float* __restrict__ I, int pitch, size_t frame_stride, int w,
-                                                    int h, void* __restrict__ Rv, size_t plane_stride,
-                                                    size_t slot_stride, int slot0, int nslots, const PolyCoef pc) {
-    using C = FastPeCfg<N>;
-    extern __shared__ __align__(16) float smem[];
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kFbTH, f = blockIdx.z;
-    const float* img = I + (size_t)f * frame_stride;
-    for (int task = tid; task < C::RG * C::NCOL; task += 256) {
-        const int rg = task / C::NCOL, col = task - rg * C::NCOL;
-        const int gx = min(max(x0 - C::HALO + col, 0), w - 1);
-        const int yb = y0 + rg * C::RPG - N;
-        float v[C::RPG + 2 * N];
-#pragma unroll
-        for (int i = 0; i < C::RPG + 2 * N; ++i) v[i] = __ldg(img + (size_t)min(max(yb + i, 0), h - 1) * pitch + gx);
-        float* dst = smem + (rg * C::RPG) * C::VP + col;
-#pragma unroll
-        for (int j = 0; j < C::RPG; ++j) {
-            const float c = v[j + N];
-            float t0 = c * pc.g[0], t1 = 0.f, t2 = 0.f;
-#pragma unroll
-            for (int k = 1; k <= N; ++k) {
-                const float up = v[j + N - k], dn = v[j + N + k];
-                const float pp = up + dn;
-                t0 = fmaf(pc.g[k], pp, t0);
-                t1 = fmaf(pc.xg[k], dn - up, t1);
-                t2 = fmaf(pc.xxg[k], pp, t2);
-            }
-            dst[j * C::VP] = t0;
-            dst[(kFbTH + j) * C::VP] = t1;
-            dst[(2 * kFbTH + j) * C::VP] = t2;
-        }
-    }
-    __syncthreads();
-    polyexp_horizontal_store<N, RH>(smem, x0, y0, f, pitch, w, h, Rv, plane_stride, slot_stride, slot0, nslots, pc);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -219,84 +277,6 @@ __global__ void __launch_bounds__(128) k_level0_blur(const T* __restrict__ src, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) { h0[j] = h1[j]; h1[j] = h2[j]; }
     }
-}
-
-// k_polyexp_l0<N, RH, T>: pyramid level 0 and its polynomial expansion in one kernel.  The uint8 (or float) frame tile
-// goes to shared memory, the exact 3x3 [1 2 1]/4 REFLECT_101 blur (scale 1) is evaluated into a second shared
-// tile at REPLICATE-clamped coordinates (what the expansion's borders need), and the two separable passes of
-// k_polyexp run from there.  Saves the level-0 image round trip through HBM (4 B/px written + read) and one launch.
-template <int N>
-struct FusedPeCfg {
-    using P = FastPeCfg<N>;
-    static constexpr int BROWS = kFbTH + 2 * N;                 // blurred tile rows
-    static constexpr int BP = P::NCOL + 4;                      // blurred tile pitch
-    static constexpr int UROWS = BROWS + 2, UP = P::NCOL + 2 + 2;   // raw tile (one more ring for the 3x3 blur)
-    static constexpr int T_FLOATS = 3 * kFbTH * P::VP;          // vertical-pass result; the raw tile aliases it
-    static constexpr size_t SMEM = (size_t)(T_FLOATS + BROWS * BP) * sizeof(float);
-    static_assert(UROWS * UP <= T_FLOATS, "raw tile must fit in the aliased region");
-};
-
-template <int N, bool RH, typename T>
-__global__ void __launch_bounds__(256, 2) k_polyexp_l0(const T* __restrict__ src, size_t src_pitch_bytes, size_t src_frame_bytes,
-                                                       int pitch, int w, int h, void* __restrict__ Rv, size_t plane_stride,
-                                                       size_t slot_stride, int slot0, int nslots, const PolyCoef pc) {
-    using C = FastPeCfg<N>;
-    using Fz = FusedPeCfg<N>;
-    extern __shared__ __align__(16) float smem[];
-    float* tbuf = smem;                                   // [3][TH][VP]   (raw tile U[UROWS][UP] lives here first)
-    float* U = smem;
-    float* Bt = smem + Fz::T_FLOATS;                      // [BROWS][BP]
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * kFbTW, y0 = blockIdx.y * kFbTH, f = blockIdx.z;
-    const char* base = (const char*)src + (size_t)f * src_frame_bytes;
-    // raw tile: U[uy][ux] = frame[reflect101(y0 - N - 1 + uy)][reflect101(x0 - HALO - 1 + ux)] (coordinates limited to
-    // [-1, size] first: anything further out is never used by an in-image blurred sample)
-    for (int e = tid; e < Fz::UROWS * (C::NCOL + 2); e += 256) {
-        const int uy = e / (C::NCOL + 2), ux = e - uy * (C::NCOL + 2);
-        const int gy = reflect101(min(max(y0 - N - 1 + uy, -1), h), h), gx = reflect101(min(max(x0 - C::HALO - 1 + ux, -1), w), w);
-        U[uy * Fz::UP + ux] = load_px((const T*)(base + (size_t)gy * src_pitch_bytes) + gx);
-    }
-    __syncthreads();
-    // blurred tile at replicate-clamped coordinates: tile index ranges that fall inside the image
-    const int ty_lo = max(0, N - y0), ty_hi = min(Fz::BROWS - 1, (h - 1) - (y0 - N));
-    const int tx_lo = max(0, C::HALO - x0), tx_hi = min(C::NCOL - 1, (w - 1) - (x0 - C::HALO));
-    for (int e = tid; e < Fz::BROWS * C::NCOL; e += 256) {
-        const int ty = e / C::NCOL, tx = e - ty * C::NCOL;
-        const int tyc = min(max(ty, ty_lo), ty_hi), txc = min(max(tx, tx_lo), tx_hi);
-        const float* q = U + tyc * Fz::UP + txc;                               // top-left of the 3x3 neighbourhood
-        float hr[3];
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) hr[dy] = q[dy * Fz::UP] * 0.25f + q[dy * Fz::UP + 1] * 0.5f + q[dy * Fz::UP + 2] * 0.25f;
-        Bt[ty * Fz::BP + tx] = hr[0] * 0.25f + hr[1] * 0.5f + hr[2] * 0.25f;   // row filter first, like cv2
-    }
-    __syncthreads();
-    // vertical pass from the blurred tile (already border-replicated)
-    for (int task = tid; task < C::RG * C::NCOL; task += 256) {
-        const int rg = task / C::NCOL, col = task - rg * C::NCOL;
-        const float* bsrc = Bt + (rg * C::RPG) * Fz::BP + col;
-        float v[C::RPG + 2 * N];
-#pragma unroll
-        for (int i = 0; i < C::RPG + 2 * N; ++i) v[i] = bsrc[i * Fz::BP];
-        float* dst = tbuf + (rg * C::RPG) * C::VP + col;
-#pragma unroll
-        for (int j = 0; j < C::RPG; ++j) {
-            const float c = v[j + N];
-            float t0 = c * pc.g[0], t1 = 0.f, t2 = 0.f;
-#pragma unroll
-            for (int k = 1; k <= N; ++k) {
-                const float up = v[j + N - k], dn = v[j + N + k];
-                const float pp = up + dn;
-                t0 = fmaf(pc.g[k], pp, t0);
-                t1 = fmaf(pc.xg[k], dn - up, t1);
-                t2 = fmaf(pc.xxg[k], pp, t2);
-            }
-            dst[j * C::VP] = t0;
-            dst[(kFbTH + j) * C::VP] = t1;
-            dst[(2 * kFbTH + j) * C::VP] = t2;
-        }
-    }
-    __syncthreads();
-    polyexp_horizontal_store<N, RH>(tbuf, x0, y0, f, pitch, w, h, Rv, plane_stride, slot_stride, slot0, nslots, pc);
 }
 
 // BGR -> gray exactly like cv2.cvtColor(COLOR_BGR2GRAY) on uint8 (/root/reference/optical_flow.py:227; SURVEY section 8 row
@@ -378,27 +358,34 @@ __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, 
         for (int x = threadIdx.x; x < d.w; x += 256) {
             const int i0 = d.ix[x];
             const float a = d.ax[x];
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            // the 4 rows of a source pixel are two packed fp32 pairs: one FFMA2 per pair and tap (coefficient broadcast)
+            const ulonglong2* srow2 = reinterpret_cast<const ulonglong2*>(srow4);
+            const f32x2_t z2 = pk2(0.f, 0.f);
+            f32x2_t b0l = z2, b0h = z2, b1l = z2, b1h = z2;
             if (i0 - rad >= 0 && i0 + 1 + rad < W) {
                 int i = i0 - rad;
-                float4 prev = srow4[pyr_slot(i)];
+                ulonglong2 prev = srow2[pyr_slot(i)];
                 for (int j = 0; j < ksize; ++j) {
                     const float kj = __ldg(kern + j);
+                    const f32x2_t k2 = pk2(kj, kj);
                     ++i;
-                    const float4 nxt = srow4[pyr_slot(i)];
-                    b0.x = fmaf(kj, prev.x, b0.x); b0.y = fmaf(kj, prev.y, b0.y); b0.z = fmaf(kj, prev.z, b0.z); b0.w = fmaf(kj, prev.w, b0.w);
-                    b1.x = fmaf(kj, nxt.x, b1.x); b1.y = fmaf(kj, nxt.y, b1.y); b1.z = fmaf(kj, nxt.z, b1.z); b1.w = fmaf(kj, nxt.w, b1.w);
+                    const ulonglong2 nxt = srow2[pyr_slot(i)];
+                    b0l = fma2(prev.x, k2, b0l); b0h = fma2(prev.y, k2, b0h);
+                    b1l = fma2(nxt.x, k2, b1l); b1h = fma2(nxt.y, k2, b1h);
                     prev = nxt;
                 }
             } else {
                 const int i1 = min(i0 + 1, W - 1);
                 for (int j = 0; j < ksize; ++j) {
                     const float kj = __ldg(kern + j);
-                    const float4 v0 = srow4[pyr_slot(reflect101(i0 - rad + j, W))], v1 = srow4[pyr_slot(reflect101(i1 - rad + j, W))];
-                    b0.x = fmaf(kj, v0.x, b0.x); b0.y = fmaf(kj, v0.y, b0.y); b0.z = fmaf(kj, v0.z, b0.z); b0.w = fmaf(kj, v0.w, b0.w);
-                    b1.x = fmaf(kj, v1.x, b1.x); b1.y = fmaf(kj, v1.y, b1.y); b1.z = fmaf(kj, v1.z, b1.z); b1.w = fmaf(kj, v1.w, b1.w);
+                    const f32x2_t k2 = pk2(kj, kj);
+                    const ulonglong2 v0 = srow2[pyr_slot(reflect101(i0 - rad + j, W))], v1 = srow2[pyr_slot(reflect101(i1 - rad + j, W))];
+                    b0l = fma2(v0.x, k2, b0l); b0h = fma2(v0.y, k2, b0h);
+                    b1l = fma2(v1.x, k2, b1l); b1h = fma2(v1.y, k2, b1h);
                 }
             }
+            const float2 b0a = up2(b0l), b0b = up2(b0h), b1a = up2(b1l), b1b = up2(b1h);
+            const float4 b0 = make_float4(b0a.x, b0a.y, b0b.x, b0b.y), b1 = make_float4(b1a.x, b1a.y, b1b.x, b1b.y);
             const float o[kPyrRows] = {(a != 0.f) ? (b0.x * (1.f - a) + b1.x * a) : b0.x, (a != 0.f) ? (b0.y * (1.f - a) + b1.y * a) : b0.y,
                                        (a != 0.f) ? (b0.z * (1.f - a) + b1.z * a) : b0.z, (a != 0.f) ? (b0.w * (1.f - a) + b1.w * a) : b0.w};
 #pragma unroll
@@ -468,8 +455,9 @@ inline bool pyr_v4_ok(const void* tmp, int tmp_pitch, size_t tmp_frame_stride, c
 
 inline bool polyexp_fast_supported(int n, int pitch) { return (n == 5 || n == 7) && (pitch % 4) == 0; }
 
-inline bool polyexp_fast_aligned(const void* R, size_t plane_stride, size_t slot_stride) {
-    return aligned16(R) && (plane_stride % 4) == 0 && (slot_stride % 4) == 0;
+// R: 128-bit stores; I: the vertical pass loads column pairs (64-bit)
+inline bool polyexp_fast_aligned(const void* R, size_t plane_stride, size_t slot_stride, const void* I, size_t frame_stride) {
+    return aligned16(R) && (plane_stride % 4) == 0 && (slot_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(I) & 7) == 0 && (frame_stride % 2) == 0;
 }
 
 template <int N, bool RH>
@@ -478,24 +466,8 @@ inline void launch_polyexp_fast_n(const float* I, int pitch, size_t frame_stride
                                   const PolyCoef& pc, cudaStream_t st) {
     using C = FastPeCfg<N>;
     cudaFuncSetAttribute(k_polyexp<N, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    dim3 g((w + kFbTW - 1) / kFbTW, (h + kFbTH - 1) / kFbTH, nf);
+    dim3 g((w + kFbTW - 1) / kFbTW, (h + kPeFastTH - 1) / kPeFastTH, nf);
     k_polyexp<N, RH><<<g, 256, C::SMEM, st>>>(I, pitch, frame_stride, w, h, R, plane_stride, slot_stride, slot0, nslots, pc);
-}
-
-template <typename T>
-inline void launch_polyexp_l0(const T* src, size_t src_pitch_bytes, size_t src_frame_bytes, int pitch, int w, int h, void* R,
-                              size_t plane_stride, size_t slot_stride, int slot0, int nslots, int nf, const PolyCoef& pc,
-                              bool r_half, cudaStream_t st) {
-    dim3 g((w + kFbTW - 1) / kFbTW, (h + kFbTH - 1) / kFbTH, nf);
-#define BF_LAUNCH_L0(NN, RHH)                                                                                             \
-    do {                                                                                                                  \
-        cudaFuncSetAttribute(k_polyexp_l0<NN, RHH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPeCfg<NN>::SMEM); \
-        k_polyexp_l0<NN, RHH, T><<<g, 256, FusedPeCfg<NN>::SMEM, st>>>(src, src_pitch_bytes, src_frame_bytes, pitch, w, h, R,    \
-                                                                       plane_stride, slot_stride, slot0, nslots, pc);      \
-    } while (0)
-    if (pc.n == 5) { if (r_half) BF_LAUNCH_L0(5, true); else BF_LAUNCH_L0(5, false); }
-    else { if (r_half) BF_LAUNCH_L0(7, true); else BF_LAUNCH_L0(7, false); }
-#undef BF_LAUNCH_L0
 }
 
 inline void launch_polyexp_fast(const float* I, int pitch, size_t frame_stride, int w, int h, void* R,

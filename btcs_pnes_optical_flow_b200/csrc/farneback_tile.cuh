@@ -666,12 +666,6 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solv
 //              conflict-free (HOFF = 4 mod 8)
 // Summation runs in row / column order (cv2: centre, then symmetric pairs): an fp32 reordering, ~1e-7 relative.
 // ---------------------------------------------------------------------------------------------------
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ float2 up2(f32x2_t v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
-__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-
 template <int MH, int TH>
 struct FastGaussCfg {
     static constexpr int HALO = (MH + 3) / 4 * 4;

@@ -137,7 +137,6 @@ def test_all_kernel_variants_agree(monkeypatch):
             ref = cv2_ref.farneback(a, b, **p)
             outs = {}
             for name, env in (("tile", {}), ("tile_f32", {"BTCSFLOW_R_STORAGE": "f32"}),
-                              ("fused_l0", {"BTCSFLOW_FUSED_L0": "1"}),
                               ("no_tmap", {"BTCSFLOW_TMAP": "0"}),            # per-line L2 prefetch instead of tensor maps
                               ("generic", {"BTCSFLOW_NO_FAST": "1"})):
                 for k, v in env.items():
@@ -151,7 +150,6 @@ def test_all_kernel_variants_agree(monkeypatch):
             assert epe(outs["tile_f32"], outs["generic"])[1] < 1e-4
             # compact storage (packed R, fp16 G + fp32 h): close to the all-fp32 path
             assert epe(outs["tile"], outs["generic"])[1] < 1e-3, epe(outs["tile"], outs["generic"])
-            assert epe(outs["fused_l0"], outs["tile"])[1] < 1e-3        # level-0 blur fused into the expansion (opt-in)
             assert np.array_equal(outs["no_tmap"], outs["tile"])        # the prefetch flavour does not touch the arithmetic
 
 

@@ -28,7 +28,6 @@ run("tile_f32", {"BTCSFLOW_R_STORAGE": "f32"}, P)
 run("exact", {}, P, exact=True)
 run("generic", {"BTCSFLOW_NO_FAST": "1"}, P)
 run("gauss", {}, G, shape=(272, 480))
-run("fused_l0", {"BTCSFLOW_FUSED_L0": "1"}, P)
 run("odd", {}, dict(B.FB_PARAMS, pyr_scale=0.7, levels=4, winsize=16, poly_n=3), shape=(131, 203))
 n = 700
 t = np.arange(n) / 30.0
