@@ -351,13 +351,20 @@ __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, 
     }
     __syncthreads();
     for (int l = 0; l < pa.nlev; ++l) {
-        const PyrLevelDesc& d = pa.lv[l];
-        const int rad = d.ksize >> 1, ksize = d.ksize;
+        // the level's descriptor and the four output row pointers are taken once per level (indexed reads of the kernel
+        // parameter and 64-bit address arithmetic per output column were half of this kernel's instructions; ncu)
+        const PyrLevelDesc d = pa.lv[l];
+        const int rad = d.ksize >> 1, ksize = d.ksize, lw = d.w;
         const float* __restrict__ kern = d.kern;
-        float* tbase = d.tmp + (size_t)f * d.tmp_frame_stride + (size_t)r0 * d.tmp_pitch;
-        for (int x = threadIdx.x; x < d.w; x += 256) {
-            const int i0 = d.ix[x];
-            const float a = d.ax[x];
+        const int* __restrict__ lix = d.ix;
+        const float* __restrict__ lax = d.ax;
+        float* trow[kPyrRows];
+#pragma unroll
+        for (int rr = 0; rr < kPyrRows; ++rr)                      // rows past the frame write (again) to the last valid row
+            trow[rr] = d.tmp + (size_t)f * d.tmp_frame_stride + (size_t)min(r0 + rr, H - 1) * d.tmp_pitch;
+        for (int x = threadIdx.x; x < lw; x += 256) {
+            const int i0 = lix[x];
+            const float a = lax[x];
             // the 4 rows of a source pixel are two packed fp32 pairs: one FFMA2 per pair and tap (coefficient broadcast)
             const ulonglong2* srow2 = reinterpret_cast<const ulonglong2*>(srow4);
             const f32x2_t z2 = pk2(0.f, 0.f);
@@ -389,8 +396,7 @@ __global__ void __launch_bounds__(256) k_pyr_h_multi(const T* __restrict__ src, 
             const float o[kPyrRows] = {(a != 0.f) ? (b0.x * (1.f - a) + b1.x * a) : b0.x, (a != 0.f) ? (b0.y * (1.f - a) + b1.y * a) : b0.y,
                                        (a != 0.f) ? (b0.z * (1.f - a) + b1.z * a) : b0.z, (a != 0.f) ? (b0.w * (1.f - a) + b1.w * a) : b0.w};
 #pragma unroll
-            for (int rr = 0; rr < kPyrRows; ++rr)
-                if (r0 + rr < H) tbase[(size_t)rr * d.tmp_pitch + x] = o[rr];
+            for (int rr = 0; rr < kPyrRows; ++rr) trow[rr][x] = o[rr];
         }
     }
 }

@@ -179,7 +179,7 @@ constexpr int kUpdRows = 4;   // 8 rows: 74 registers, slower (18.1 vs 17.3 ms p
 // -- next row's gather in flight in registers, 64 registers, 4 CTAs/SM -- took 1.45 ms per 64-pair 1080p launch, this one
 // 1.23 ms; the kernel is latency-bound and responds to resident warps; profiles/r2_experiments.txt.)
 template <bool RH>
-__global__ void __launch_bounds__(256, RH ? 6 : 4) k_update(const UpdateArgs a) {
+__global__ void __launch_bounds__(256, RH ? 6 : 5) k_update(const UpdateArgs a) {
     // block = 64 columns x (4 x kUpdRows) rows; 1-D grid in decode_cta order
     const TilePos tp = decode_cta(blockIdx.x, (a.w + 63) / 64, (a.h + 4 * kUpdRows - 1) / (4 * kUpdRows), a.np, a.pair_group);
     const int x = tp.bx * 64 + threadIdx.x;
@@ -274,6 +274,25 @@ __global__ void __launch_bounds__(256, RH ? 6 : 4) k_update(const UpdateArgs a) 
             if (yb + k < h) MView<true>::store_at(pg + k * (kMbW * 2), ph + k * (kMbW * 4), m);
         }
     } else {
+        // exact plans: the same L1 prefetch over the five fp32 planes (two tap rows each + the R0 pixel)
+        if (a.np > 0) {
+            const float* R0f = static_cast<const float*>(R0);
+            const float* R1f = static_cast<const float*>(R1);
+#pragma unroll
+            for (int k = 0; k < kUpdRows; ++k) {
+                const int yy = min(yb + k, h - 1);
+                const int x1 = __float2int_rd((float)x + fl[k].x), y1 = __float2int_rd((float)yy + fl[k].y);
+                const int cx = max(min(x1, w - 2), 0), cy = max(min(y1, h - 2), 0);
+                const float* pa = R1f + (unsigned)cy * pitch + (unsigned)cx;
+                const float* pq = R0f + (unsigned)yy * pitch + (unsigned)x;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + (size_t)c * plane));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + (size_t)c * plane + pitch));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pq + (size_t)c * plane));
+                }
+            }
+        }
 #pragma unroll
         for (int k = 0; k < kUpdRows; ++k) {
             const int y = yb + k;

@@ -172,6 +172,35 @@ def test_widths_not_multiple_of_4(monkeypatch):
         assert epe(got, gen)[1] < 5e-3, (w, epe(got, gen))          # compact vs fp32 storage, same border handling
 
 
+def test_gaussian_window_ragged_sizes(monkeypatch):
+    """OPTFLOW_FARNEBACK_GAUSSIAN through the packed-pair tile kernel: odd widths (the G22 column pairs and the polynomial
+    expansion's column pairs straddle the right edge), heights that leave partial and edge-only tiles, compact and exact
+    plans, against cv2 and against the runtime-parameter kernel."""
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    for (h, w, win, pn) in ((150, 317, 21, 7), (97, 131, 15, 5), (40, 66, 9, 5), (212, 258, 25, 7)):
+        p = dict(B.FB_PARAMS, winsize=win, poly_n=pn, poly_sigma=1.5 if pn == 7 else 1.1, flags=256)
+        a, b = textured(h, w, w + h), textured(h, w, w + h, shift=(1.1, -0.7))
+        ref = cv2_ref.farneback(a, b, **p)
+        outs = {}
+        for name, exact, env in (("compact", False, {}), ("exact", True, {}), ("generic", True, {"BTCSFLOW_NO_FAST": "1"})):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            with B.FlowPlan(w, h, p, exact=exact) as plan:
+                outs[name] = plan.flow_pair(a, b)
+            for k in env:
+                monkeypatch.delenv(k)
+            band = 2 * (win // 2) + 2
+            if min(h, w) > 2 * band + 2:
+                mean, inner, edge = epe_banded(outs[name], ref, band)
+                assert mean <= MEAN_TIGHT and inner <= MAX_TIGHT and edge <= 0.25, (name, h, w, p, mean, inner, edge)
+            else:
+                mean, mx = epe(outs[name], ref)
+                assert mean <= MEAN_TIGHT and mx <= 0.25, (name, h, w, p, mean, mx)
+        assert epe(outs["exact"], outs["generic"])[1] < 1e-4, (h, w, epe(outs["exact"], outs["generic"]))
+        assert epe(outs["compact"], outs["generic"])[1] < 5e-3, (h, w, epe(outs["compact"], outs["generic"]))
+
+
 def test_1080p_full_size_properties():
     """BASELINE full size: parity on one pair + size-independent properties (translation recovery, determinism)."""
     import btcs_pnes_optical_flow_b200 as B

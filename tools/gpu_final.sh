@@ -1,6 +1,7 @@
 #!/bin/bash
 # Final measurements of a round on one GPU: GPU tests, default bench line (C2, with parity and exact plan), the other configs,
-# strong scaling at N = 1, launch list and ncu --set full capture of the dominant kernel.
+# strong scaling at N = 1 and the launch list.  The ncu --set full captures are tools/gpu_final_ncu.sh (a separate call: gpurun
+# brings back at most 64 MiB).
 tag=${1:-final}
 out=gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -15 > $out/${tag}_tests.log; tail -3 $out/${tag}_tests.log
@@ -9,10 +10,6 @@ python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_be
 for c in C1 C4 C5; do python bench.py --config $c --steps 5 --warmup 3 > $out/${tag}_bench_$c.json 2> $out/${tag}_bench_$c.err; tail -c 300 $out/${tag}_bench_$c.err; done
 python bench.py --scaling strong --clips 64 --frames 300 --steps 2 --warmup 1 > $out/${tag}_strong1.json 2> $out/${tag}_strong1.err; tail -c 300 $out/${tag}_strong1.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-exact --no-parity > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name regex:k_blur_solve_box --launch-skip 20 --launch-count 4 \
-    -o $out/${tag}_box python bench.py --steps 1 --warmup 1 --no-exact --no-parity > $out/${tag}_ncu.log 2>&1
-ncu --set full --clock-control none --kernel-name regex:"k_update|k_polyexp|k_pyr|k_level0" --launch-skip 30 --launch-count 12 \
-    -o $out/${tag}_others python bench.py --steps 1 --warmup 1 --no-exact --no-parity > /dev/null 2>&1
 python - <<PY
 import json
 for n in ("bench", "bench_C1", "bench_C4", "bench_C5", "strong1", "ref"):

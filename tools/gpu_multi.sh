@@ -1,7 +1,7 @@
 #!/bin/bash
 # Multi-GPU measurements on one box: bash tools/gpu_multi.sh <tag> <N>
 tag=$1; n=$2; out=gpurun_out
-if [ "$n" = "2" ]; then python -m pytest tests/test_gpu_distributed.py -m gpu -q 2>&1 | tail -3; fi
+if [ "$n" = "2" ]; then python -m pytest tests/test_gpu_distributed.py -m gpu -q -rA > $out/${tag}_nccl_test.log 2>&1; grep -E "PASSED|FAILED|SKIPPED|passed|failed|skipped" $out/${tag}_nccl_test.log | tail -4; fi
 python bench.py --gpus $n --steps 10 --warmup 3 --no-exact --no-parity > $out/${tag}_weak_n$n.json 2> $out/${tag}_weak_n$n.err; tail -c 300 $out/${tag}_weak_n$n.err
 python bench.py --gpus $n --scaling strong --clips 64 --frames 300 --steps 2 --warmup 1 > $out/${tag}_strong_n$n.json 2> $out/${tag}_strong_n$n.err; tail -c 300 $out/${tag}_strong_n$n.err
 python - <<PY

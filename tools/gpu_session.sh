@@ -13,7 +13,7 @@ for v in "${variants[@]}"; do
 import json
 try:
     l=[x for x in open("$out/${tag}_bench_$name.log") if x.startswith("{")][-1]; d=json.loads(l)
-    r=d["roofline"]; print("$name", round(d["value"]), round(d["e2e"]["value"]), "frac %.3f last %.3f ms upd %.3f ms stage %.3f pipe %.3f" % (r["frac"], r["last_iteration"]["avg_launch_ms"], r["avg_launch_ms"], r["stage_frac"], r["pipeline_frac"]), {k: round(v,2) for k,v in r["stages_ms_per_step"].items()})
+    r=d["roofline"]; print("$name", round(d["value"]), round(d["e2e"]["value"]), "frac %.3f last %.3f ms upd %.3f ms stage %.3f pipe %.3f" % (r["frac"], r["last_iteration"]["avg_launch_ms"], r["avg_launch_ms"], r["stage_frac"], r["pipeline_frac"]), {k: round(v,2) for k,v in r["stages_ms_timed_region"].items()})
 except Exception as e: print("$name failed", e)
 PY
 done
