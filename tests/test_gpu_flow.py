@@ -201,6 +201,30 @@ def test_gaussian_window_ragged_sizes(monkeypatch):
         assert epe(outs["compact"], outs["generic"])[1] < 5e-3, (h, w, epe(outs["compact"], outs["generic"]))
 
 
+def test_every_compiled_window():
+    """Every half window with a compile-time tile kernel (winsize 4 .. 33, box and Gaussian; compact and exact storage) on an
+    odd-sized frame: each instantiation has its own halo / chunk geometry (odd and even leading offsets, plane strides)."""
+    import btcs_pnes_optical_flow_b200 as B
+    from oracle import cv2_ref
+    h, w = 97, 131
+    a, b = textured(h, w, 5), textured(h, w, 5, shift=(0.9, -0.6))
+    for win in range(4, 34):
+        for flags in (0, 256):
+            p = dict(B.FB_PARAMS, winsize=win, levels=1, iterations=2, flags=flags)
+            ref = cv2_ref.farneback(a, b, **p)
+            for exact in (False, True):
+                with B.FlowPlan(w, h, p, exact=exact) as plan:
+                    got = plan.flow_pair(a, b)
+                assert np.isfinite(got).all(), (win, flags, exact)
+                band = 2 * (win // 2) + 2
+                if min(h, w) > 2 * band + 8:
+                    mean, inner, edge = epe_banded(got, ref, band)
+                    assert mean <= MEAN_TIGHT and inner <= MAX_TIGHT and edge <= 0.25, (win, flags, exact, mean, inner, edge)
+                else:
+                    mean, mx = epe(got, ref)
+                    assert mean <= MEAN_TIGHT and mx <= 0.25, (win, flags, exact, mean, mx)
+
+
 def test_1080p_full_size_properties():
     """BASELINE full size: parity on one pair + size-independent properties (translation recovery, determinism)."""
     import btcs_pnes_optical_flow_b200 as B
