@@ -696,7 +696,11 @@ int bf_plan_create_ex(const bf_params* params, int width, int height, int max_pa
         const bool want_f32 = (flags & BF_PLAN_EXACT_F32) || (rs && strcmp(rs, "f32") == 0);
         // packed fp16 coefficients need the compile-time polyexp kernels (poly_n 5 / 7) and bounded (uint8) input
         // (and frames of at least 4 x 2 pixels: the packed gather reads a 2 x 2 footprint at immediate offsets)
-        p->r_half = p->use_fast && !want_f32 && (params->poly_n == 5 || params->poly_n == 7) && width >= 4 && height >= 2;
+        // Gaussian windows below 8 pixels (sigma <= 0.9) concentrate the weight on one or two samples: in flat regions of the
+        // attenuated border ring the fp16 G terms become subnormal and the compact result moves by up to 0.4 px there
+        // (tools/window_sweep.py).  Those windows are cheap anyway: they take the all-fp32 storage.
+        const bool tiny_gauss = (params->flags & BF_OPTFLOW_FARNEBACK_GAUSSIAN) && params->winsize < 8;
+        p->r_half = p->use_fast && !want_f32 && !tiny_gauss && (params->poly_n == 5 || params->poly_n == 7) && width >= 4 && height >= 2;
         cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     }
 
