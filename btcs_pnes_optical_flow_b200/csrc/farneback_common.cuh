@@ -202,8 +202,11 @@ __device__ __forceinline__ unsigned pack_h2_sat(float lo, float hi) { unsigned d
 __device__ __forceinline__ unsigned short f2h_sat(float v) { unsigned short d; asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(d) : "f"(v)); return d; }
 __device__ __forceinline__ float h2f(unsigned short h) { float d; asm("cvt.f32.f16 %0, %1;" : "=f"(d) : "h"(h)); return d; }
 
-// ---- packed fp32 pairs (sm_100a FFMA2 / FMUL2: two IEEE fp32 operations per issue slot; a scalar operand is broadcast when
-// both halves of a pair are the same register) ---------------------------------------------------------------------------
+// ---- packed fp32 pairs (sm_100a fma/add/mul.rn.f32x2 -> FFMA2 / FADD2 / FMUL2: two IEEE fp32 operations per instruction; a scalar
+// operand is broadcast when both halves of a pair are the same register).  Measured (tools/ubench_f32x2.cu): the same lane rate as
+// scalar FFMA (128 per clock and SM) AND the same issue cost -- 8 FFMA2 + 16 IADD take as long as 16 FFMA + 16 IADD -- so a
+// packed instruction buys nothing by itself.  What it gives the kernels that use it is the pair-wide task: one load, one
+// conversion, one address and one loop step feed two accumulators, and the code stays half as long. ----------------------------
 typedef unsigned long long f32x2_t;
 __device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ float2 up2(f32x2_t v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }

@@ -10,8 +10,9 @@ namespace bf {
 
 // ---------------------------------------------------------------------------------------------------
 // k_polyexp<N>: separable polynomial expansion with compile-time poly_n.  Tile 128 x 24, 256 threads.
-// The kernel is bound by the issue of its FP32 operations (ncu: 72 % of 133 instructions per pixel were FFMA / FADD /
-// FMUL), so both passes work on packed fp32 pairs (FFMA2 / FADD2, farneback_common.cuh):
+// 72 % of the first version's 133 instructions per pixel were FFMA / FADD / FMUL and the rest per-element overhead; both
+// passes now work on packed fp32 pairs (FFMA2 / FADD2, farneback_common.cuh -- same issue cost as two scalar operations, but
+// one load, address and loop step per pair):
 //   vertical pass   task = (column pair, 8-row group): 64-bit loads straight from global (rows clamped = replicate), the
 //                   8 + 2N row pairs live in registers; per tap one packed add, one packed subtract, three packed FMAs
 //   shared memory   plane P01 = (t0, t1) interleaved per column, stored as 16-byte chunks of two columns, even chunks

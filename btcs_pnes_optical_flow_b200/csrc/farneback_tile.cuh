@@ -651,11 +651,13 @@ __global__ void __launch_bounds__(256, FastBoxCfg<MH, TH, RH>::CTAS) k_blur_solv
 // ---------------------------------------------------------------------------------------------------
 // k_blur_solve_gauss<MH>: the same fused iteration for OPTFLOW_FARNEBACK_GAUSSIAN (separable float32
 // Gaussian window, sigma = 0.3*MH, replicate borders) -- config C4 runs winsize 21 (MH = 10).  No running sums here:
-// every output is a (2MH+1)-tap weighted sum, and the kernel is bound by the ISSUE of those FP32 operations (ncu: the
-// scalar version spent 280 + 130 instructions per pixel in the two passes).  Both passes therefore work on PAIRS of fp32
-// values with the packed sm_100a instructions (fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2: two IEEE fp32 operations
-// per issue slot, coefficient operand broadcast), in "scatter" form: every loaded value is multiplied into the outputs it
-// contributes to and then dropped, so neither pass keeps a window in registers.
+// every output is a (2MH+1)-tap weighted sum, and the kernel is bound by instruction issue (ncu: the first version -- one
+// scalar column per task, the 2MH+1 window rows in registers -- spent 280 + 130 instructions per pixel in the two passes, less
+// than half of them arithmetic: window shifting, local-memory spills, per-element loads, conversions and addresses).  Both
+// passes therefore work on PAIRS of fp32 values (fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2, coefficient operand broadcast)
+// in "scatter" form: every loaded value is multiplied into the outputs it contributes to and then dropped, so neither pass
+// keeps a window in registers, and every load / conversion / address serves two accumulators.  (A packed instruction issues
+// at the cost of two scalar ones -- tools/ubench_f32x2.cu -- the gain is the overhead that disappears: 542 -> 344 instr/px.)
 //   pairs      A = (G11, G12) and B = (h1, h2) of one pixel; the fifth channel (G22) is paired over two adjacent columns
 //              in the vertical pass and runs scalar in the horizontal one
 //   phase 1    one task = one column of a channel pair (or a column pair of G22): TH + 2MH loads, TH accumulator pairs,
