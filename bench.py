@@ -221,6 +221,10 @@ def roofline_block(prof, ms_total, fine, iters, peak, peak_src, value_per_gpu, b
     upd, last, first = st["iter_update"], st["iter_last"], st["update"]
     ach = gbs(upd["pairs"], 56, upd["ms"])
     traffic = measured_traffic()
+    # the capture is of the 1080p box-window kernel at 64 pairs per launch: other frame sizes, windows or batches get null
+    if traffic and not ((fine["w"], fine["h"]) == (1920, 1080) and "box<7" in kernel_name and "compact" in kernel_name
+                        and upd["launches"] and upd["pairs"] == traffic.get("pairs_per_launch", 64) * upd["launches"]):
+        traffic = None
     block = {
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
         "traffic": (traffic["iter_update_dram_bytes_per_pair"] * upd["pairs"] / max(upd["launches"], 1)) if traffic else None,
