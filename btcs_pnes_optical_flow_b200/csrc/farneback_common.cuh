@@ -264,31 +264,34 @@ __device__ __forceinline__ void update_issue_h(const uint4* __restrict__ r0px, c
     }
 }
 
+// q = R0 at the pixel; u00, u01 = top taps, u10, u11 = bottom taps of the clamped footprint
 template <bool BORDER>
-__device__ __forceinline__ void update_finish_h(const UpdTaps& t, int w, int h, int x, int y, MOut<true>& o) {
-    const float gy = 1.f - t.fy;
-    const float a00 = t.gx * gy, a01 = t.fx * gy, a10 = t.gx * t.fy, a11 = t.fx * t.fy;
+__device__ __forceinline__ void update_finish_core(const uint4& tq, const uint4& t00, const uint4& t01, const uint4& t10, const uint4& t11,
+                                                   float tfx, float tgx, float tfy, float tsa, float tdx, float tdy, int w, int h, int x,
+                                                   int y, MOut<true>& o) {
+    const float gy = 1.f - tfy;
+    const float a00 = tgx * gy, a01 = tfx * gy, a10 = tgx * tfy, a11 = tfx * tfy;
     // linear terms: fp32 taps, fp32 weights
-    const float rb0 = a00 * __uint_as_float(t.u00.x) + a01 * __uint_as_float(t.u01.x) + a10 * __uint_as_float(t.u10.x) + a11 * __uint_as_float(t.u11.x);
-    const float rb1 = a00 * __uint_as_float(t.u00.y) + a01 * __uint_as_float(t.u01.y) + a10 * __uint_as_float(t.u10.y) + a11 * __uint_as_float(t.u11.y);
+    const float rb0 = a00 * __uint_as_float(t00.x) + a01 * __uint_as_float(t01.x) + a10 * __uint_as_float(t10.x) + a11 * __uint_as_float(t11.x);
+    const float rb1 = a00 * __uint_as_float(t00.y) + a01 * __uint_as_float(t01.y) + a10 * __uint_as_float(t10.y) + a11 * __uint_as_float(t11.y);
     // quadratic terms: fp16 taps x fp16 weights accumulated in fp32 (the weights lose 2^-12 relative, far below the storage
     // rounding of the taps themselves)
     unsigned short w00, w01, w10, w11;
     split_h2(pack_h2_sat(a00, a01), w00, w01);
     split_h2(pack_h2_sat(a10, a11), w10, w11);
     unsigned short yy00, xx00, yy01, xx01, yy10, xx10, yy11, xx11, xy00, xy01, xy10, xy11, z;
-    split_h2(t.u00.z, yy00, xx00); split_h2(t.u01.z, yy01, xx01); split_h2(t.u10.z, yy10, xx10); split_h2(t.u11.z, yy11, xx11);
-    split_h2(t.u00.w, xy00, z); split_h2(t.u01.w, xy01, z); split_h2(t.u10.w, xy10, z); split_h2(t.u11.w, xy11, z);
+    split_h2(t00.z, yy00, xx00); split_h2(t01.z, yy01, xx01); split_h2(t10.z, yy10, xx10); split_h2(t11.z, yy11, xx11);
+    split_h2(t00.w, xy00, z); split_h2(t01.w, xy01, z); split_h2(t10.w, xy10, z); split_h2(t11.w, xy11, z);
     const float ayy = fh_fma(yy11, w11, fh_fma(yy10, w10, fh_fma(yy01, w01, fh_fma(yy00, w00, 0.f))));
     const float axx = fh_fma(xx11, w11, fh_fma(xx10, w10, fh_fma(xx01, w01, fh_fma(xx00, w00, 0.f))));
     const float axy = fh_fma(xy11, w11, fh_fma(xy10, w10, fh_fma(xy01, w01, fh_fma(xy00, w00, 0.f))));
     unsigned short qyy, qxx, qxy;
-    split_h2(t.q.z, qyy, qxx); split_h2(t.q.w, qxy, z);
-    float r4 = fh_add(qyy, ayy) * t.sa;
-    float r5 = fh_add(qxx, axx) * t.sa;
-    float r6 = fh_add(qxy, axy) * (t.sa * 0.5f);
-    float b2 = (__uint_as_float(t.q.x) - rb0) * 0.5f;
-    float b3 = (__uint_as_float(t.q.y) - rb1) * 0.5f;
+    split_h2(tq.z, qyy, qxx); split_h2(tq.w, qxy, z);
+    float r4 = fh_add(qyy, ayy) * tsa;
+    float r5 = fh_add(qxx, axx) * tsa;
+    float r6 = fh_add(qxy, axy) * (tsa * 0.5f);
+    float b2 = (__uint_as_float(tq.x) - rb0) * 0.5f;
+    float b3 = (__uint_as_float(tq.y) - rb1) * 0.5f;
     if (BORDER && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
         const float sc = border_w(x, w) * border_w(y, h);
         b2 *= sc; b3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
@@ -300,8 +303,13 @@ __device__ __forceinline__ void update_finish_h(const UpdTaps& t, int w, int h, 
     split_h2(o.g01, hg11, hg12);
     const float q11 = h2f(hg11), q12 = h2f(hg12), q22 = h2f(o.g2);
     // h = A (b0 - b1)/2 + G d with the ROUNDED G (see the note on consistent rounding above)
-    o.h1 = fmaf(q12, t.dx, fmaf(q11, t.dy, fmaf(r6, b3, r4 * b2)));
-    o.h2 = fmaf(q22, t.dx, fmaf(q12, t.dy, fmaf(r5, b3, r6 * b2)));
+    o.h1 = fmaf(q12, tdx, fmaf(q11, tdy, fmaf(r6, b3, r4 * b2)));
+    o.h2 = fmaf(q22, tdx, fmaf(q12, tdy, fmaf(r5, b3, r6 * b2)));
+}
+
+template <bool BORDER>
+__device__ __forceinline__ void update_finish_h(const UpdTaps& t, int w, int h, int x, int y, MOut<true>& o) {
+    update_finish_core<BORDER>(t.q, t.u00, t.u01, t.u10, t.u11, t.fx, t.gx, t.fy, t.sa, t.dx, t.dy, w, h, x, y, o);
 }
 
 // one-piece form (runtime-parameter kernel, tile tails that also write flow)
